@@ -1,0 +1,181 @@
+/*
+ * pixelsplat_b200.h -- C ABI of the B200-native render hot path of pixelSplat.
+ *
+ * Drop-in boundary.  The reference binds its rasterizer through the
+ * Python extension `diff_gaussian_rasterization` (imported at
+ * /root/reference/src/model/decoder/cuda_splatting.py:5-8, called at :99-124 and :192-217);
+ * that extension's own C++ entry points are `_C.rasterize_gaussians` /
+ * `_C.rasterize_gaussians_backward` (un-vendored dependency, requirements.txt:17).  The two
+ * functions below replace exactly those two, generalised to a batch of scenes x views so that
+ * `render_cuda`'s per-view Python loop (cuda_splatting.py:91-126), its two `.item()` host syncs
+ * (:102-103), the SH permute copy (:75), the covariance triu gather (:123) and
+ * DecoderSplattingCUDA's `repeat` of every Gaussian tensor per view
+ * (decoder_splatting_cuda.py:53-56) all disappear.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless it says "host"; nothing here is a torch type;
+ *   - all work is enqueued on `stream`; no call synchronises the device;
+ *   - every function returns PS_OK (0) or a PS_ERR_* code; ps_last_error() gives the text;
+ *   - matrices are 16 floats, column-major (element [4*col+row]) -- the flattened row-major
+ *     transpose that cuda_splatting.py:85-87 builds;
+ *   - fp32 throughout; indices uint32; sort keys uint64.
+ */
+#ifndef PIXELSPLAT_B200_H
+#define PIXELSPLAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PS_API __attribute__((visibility("default")))
+#else
+#define PS_API
+#endif
+
+#define PS_OK 0
+#define PS_ERR_INVALID_ARGUMENT 1
+#define PS_ERR_CUDA 2
+#define PS_ERR_UNSUPPORTED 3
+
+#define PS_TILE 16 /* upstream BLOCK_X = BLOCK_Y */
+
+/* sh_layout */
+#define PS_SH_M3 0 /* [P, M, 3]  what GaussianRasterizer.forward receives (cuda_splatting.py:75) */
+#define PS_SH_3M 1 /* [P, 3, M]  pixelSplat's native Gaussians.harmonics (model/types.py:11)    */
+/* cov_layout */
+#define PS_COV_TRIU6 0 /* [P, 6]  xx,xy,xz,yy,yz,zz = cov3D_precomp (cuda_splatting.py:115,123) */
+#define PS_COV_3X3 1   /* [P, 3, 3]  Gaussians.covariances; only the upper triangle is read, and
+                          only the upper triangle receives gradient (autograd of the triu gather) */
+
+typedef struct ps_raster_desc {
+    int32_t n_scenes;        /* S: independent Gaussian sets                                   */
+    int32_t views_per_scene; /* V: cameras that share one Gaussian set                         */
+    int32_t n_gaussians;     /* P per scene                                                    */
+    int32_t sh_coeffs;       /* M (1..25) when colours come from SH; 0 = colors_precomp [P,3]  */
+    int32_t sh_degree;       /* active degree, 0..4, (sh_degree+1)^2 <= M                      */
+    int32_t sh_layout;       /* PS_SH_*                                                        */
+    int32_t cov_layout;      /* PS_COV_*                                                       */
+    int32_t height, width;   /* image size in pixels                                           */
+    int32_t sort_impl;       /* 0 = native per-tile radix sort; 1 = CUB segmented sort (debug)  */
+    int64_t instance_capacity; /* room, in (tile,Gaussian) instances, summed over all S*V views */
+} ps_raster_desc;
+
+/* Per-call inputs. Camera arrays are indexed by flat view id  vid = scene * V + view. */
+typedef struct ps_raster_inputs {
+    const float *means;      /* [S, P, 3]                                                      */
+    const float *cov;        /* [S, P, 6] or [S, P, 3, 3] (cov_layout)                         */
+    const float *opacities;  /* [S, P]                                                         */
+    const float *sh;         /* [S, P, M, 3] / [S, P, 3, M] (sh_layout), or colours [S, P, 3]  */
+    const float *viewmatrix; /* [S*V, 16] world->camera, column-major                          */
+    const float *projmatrix; /* [S*V, 16] world->clip (view @ proj), column-major              */
+    const float *campos;     /* [S*V, 3]                                                       */
+    const float *tanfov;     /* [S*V, 2] tan(fov_x/2), tan(fov_y/2)                            */
+    const float *background; /* [S*V, 3]                                                       */
+    const float *scene_scale; /* [S*V] or NULL: means*=s, cov*=s*s before use -- the
+                                 scale_invariant rescale of cuda_splatting.py:64-71, fused     */
+} ps_raster_inputs;
+
+/* Opaque state that lives from forward to backward (the analogue of upstream's geomBuffer /
+ * binningBuffer / imgBuffer byte tensors).  The caller allocates; sizes from ps_raster_sizes. */
+typedef struct ps_raster_state {
+    void *geom;    size_t geom_bytes;
+    void *binning; size_t binning_bytes;
+    void *image;   size_t image_bytes;
+} ps_raster_state;
+
+typedef struct ps_raster_sizes {
+    size_t geom_bytes, binning_bytes, image_bytes, backward_bytes;
+} ps_raster_sizes;
+
+/* Byte offsets of the intermediates inside the state buffers (parity tests read them;
+ * "bit-exact tile/bin indices" is checked on keys / tile_start / tile_count). */
+typedef struct ps_raster_layout {
+    /* geom */
+    size_t depth;         /* f32  [S*V*P]                                                      */
+    size_t radii;         /* i32  [S*V*P]                                                      */
+    size_t xy;            /* f32x2                                                             */
+    size_t conic_opacity; /* f32x4                                                             */
+    size_t rgb;           /* f32x4 (r,g,b,unused)                                              */
+    size_t rect;          /* u16x4 (minx,miny,maxx,maxy) in tiles                              */
+    size_t clamped;       /* u8   bit c set = channel c was clamped to 0                       */
+    size_t tile_count;    /* u32  [S*V*tiles]                                                  */
+    size_t tile_start;    /* u32  [S*V*tiles] exclusive scan, global instance offsets          */
+    size_t tile_cursor;   /* u32  scratch                                                      */
+    size_t n_instances;   /* i64  [1] total instances needed (may exceed capacity)             */
+    /* binning */
+    size_t keys;          /* u64  [capacity]  per tile sorted (float_bits(depth)<<32 | gaussian) */
+    size_t keys_alt;      /* u64  [capacity]  scratch                                          */
+    /* image */
+    size_t final_T;       /* f32  [S*V*H*W]                                                    */
+    size_t n_contrib;     /* u32  [S*V*H*W]                                                    */
+} ps_raster_layout;
+
+typedef struct ps_raster_grads {
+    float *d_means;     /* [S, P, 3]                                                           */
+    float *d_cov;       /* same layout as cov                                                  */
+    float *d_opacities; /* [S, P]                                                              */
+    float *d_sh;        /* same layout as sh (or [S, P, 3] for colours)                        */
+    float *d_means2d;   /* [S*V, P, 3] or NULL: upstream's screen-space gradient (x, y, 0)     */
+} ps_raster_grads;
+
+PS_API int ps_version(void);
+PS_API const char *ps_last_error(void); /* thread-local, valid until the next failing call */
+
+/* Instrumentation used by bench.py: number of kernels this library has launched so far, and
+ * optional per-stage CUDA-event timing (on the launching stream) of the most recent
+ * forward + backward pair: ms[7] = preprocess, count-scan + scatter, sort, composite forward,
+ * gradient zero-fill, composite backward, preprocess backward. */
+PS_API unsigned long long ps_launch_count(void);
+PS_API void ps_timing_enable(int on);
+PS_API int ps_timing_read(float *ms);
+
+/* Workspace sizes / layout for a descriptor. */
+PS_API int ps_raster_sizes_query(const ps_raster_desc *desc, ps_raster_sizes *out);
+PS_API int ps_raster_layout_query(const ps_raster_desc *desc, ps_raster_layout *out);
+
+/*
+ * Camera set-up for n_views views in one launch: the device-side restatement of
+ * cuda_splatting.py:64-87 (scale-invariant rescale of the extrinsics translation and near/far,
+ * get_fov, get_projection_matrix, extrinsics.inverse(), view @ proj) without the per-view
+ * `.item()` host syncs of :102-103.
+ *   extrinsics [n,4,4] camera-to-world row-major, intrinsics [n,3,3] normalised, near/far [n]
+ *   -> viewmatrix/projmatrix [n,16] (column-major), campos [n,3], tanfov [n,2],
+ *      scene_scale [n] (= 1/near when scale_invariant, else 1; feed to ps_raster_inputs).
+ */
+PS_API int ps_camera_setup(int32_t n_views, const float *extrinsics, const float *intrinsics,
+                           const float *near_plane, const float *far_plane, int32_t scale_invariant,
+                           float *viewmatrix, float *projmatrix, float *campos, float *tanfov,
+                           float *scene_scale, void *stream);
+
+/*
+ * Forward: preprocess -> per-tile count/scan -> scatter -> per-tile radix sort -> composite.
+ * Replaces _C.rasterize_gaussians for S*V views at once.
+ *   out_color      [S*V, 3, H, W]
+ *   out_radii      [S*V, P] int32 or NULL
+ *   n_instances_host  pinned HOST int64 or NULL: receives the instance count asynchronously
+ *                  (valid once `stream` reaches this point).  If it exceeds
+ *                  desc->instance_capacity the binning was truncated and out_color is INVALID:
+ *                  the caller must re-run with a larger capacity (pixelsplat_b200.rasterizer does).
+ */
+PS_API int ps_raster_forward(const ps_raster_desc *desc, const ps_raster_inputs *in,
+                      const ps_raster_state *state, float *out_color, int32_t *out_radii,
+                      int64_t *n_instances_host, void *stream);
+
+/*
+ * Backward: composite backward (warp-reduced, one atomic per (tile, Gaussian)) ->
+ * per-Gaussian cov2D / projection / SH backward summed over the V views of a scene.
+ * Replaces _C.rasterize_gaussians_backward.  `scratch` has ps_raster_sizes.backward_bytes.
+ */
+PS_API int ps_raster_backward(const ps_raster_desc *desc, const ps_raster_inputs *in,
+                       const ps_raster_state *state, const float *d_color /* [S*V,3,H,W] */,
+                       void *scratch, size_t scratch_bytes, const ps_raster_grads *grads,
+                       void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIXELSPLAT_B200_H */

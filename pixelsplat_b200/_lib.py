@@ -1,0 +1,121 @@
+"""ctypes binding of include/pixelsplat_b200.h.
+
+There is no fallback: if the CUDA library is missing, importing this module raises.  Build it
+with `python -c "import __graft_entry__ as g; g.build()"` or `make -C pixelsplat_b200/csrc`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "_C" / "libpixelsplat_b200.so"
+
+PS_OK = 0
+PS_SH_M3, PS_SH_3M = 0, 1
+PS_COV_TRIU6, PS_COV_3X3 = 0, 1
+TILE = 16
+
+_ERR_NAMES = {1: "PS_ERR_INVALID_ARGUMENT", 2: "PS_ERR_CUDA", 3: "PS_ERR_UNSUPPORTED"}
+
+
+class RasterDesc(ctypes.Structure):
+    _fields_ = [
+        ("n_scenes", ctypes.c_int32), ("views_per_scene", ctypes.c_int32),
+        ("n_gaussians", ctypes.c_int32), ("sh_coeffs", ctypes.c_int32),
+        ("sh_degree", ctypes.c_int32), ("sh_layout", ctypes.c_int32),
+        ("cov_layout", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
+        ("sort_impl", ctypes.c_int32), ("instance_capacity", ctypes.c_int64),
+    ]
+
+
+class RasterInputs(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        "means", "cov", "opacities", "sh", "viewmatrix", "projmatrix", "campos", "tanfov",
+        "background", "scene_scale")]
+
+
+class RasterState(ctypes.Structure):
+    _fields_ = [("geom", ctypes.c_void_p), ("geom_bytes", ctypes.c_size_t),
+                ("binning", ctypes.c_void_p), ("binning_bytes", ctypes.c_size_t),
+                ("image", ctypes.c_void_p), ("image_bytes", ctypes.c_size_t)]
+
+
+class RasterSizes(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_size_t) for n in (
+        "geom_bytes", "binning_bytes", "image_bytes", "backward_bytes")]
+
+
+class RasterLayout(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_size_t) for n in (
+        "depth", "radii", "xy", "conic_opacity", "rgb", "rect", "clamped", "tile_count",
+        "tile_start", "tile_cursor", "n_instances", "keys", "keys_alt", "final_T", "n_contrib")]
+
+
+class RasterGrads(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        "d_means", "d_cov", "d_opacities", "d_sh", "d_means2d")]
+
+
+EXPORTS = ("ps_version", "ps_last_error", "ps_raster_sizes_query", "ps_raster_layout_query",
+           "ps_raster_forward", "ps_raster_backward", "ps_camera_setup", "ps_launch_count",
+           "ps_timing_enable", "ps_timing_read")
+
+
+class NativeLibraryMissing(ImportError):
+    pass
+
+
+def _load() -> ctypes.CDLL:
+    if not LIB_PATH.exists():
+        raise NativeLibraryMissing(
+            f"{LIB_PATH} not found: the sm_100a CUDA library is not built. Run "
+            f"`make -C {_PKG / 'csrc'}` (or __graft_entry__.build()). There is no CPU fallback.")
+    lib = ctypes.CDLL(str(LIB_PATH))
+    lib.ps_version.restype = ctypes.c_int
+    lib.ps_last_error.restype = ctypes.c_char_p
+    P = ctypes.POINTER
+    lib.ps_raster_sizes_query.argtypes = [P(RasterDesc), P(RasterSizes)]
+    lib.ps_raster_layout_query.argtypes = [P(RasterDesc), P(RasterLayout)]
+    lib.ps_raster_forward.argtypes = [P(RasterDesc), P(RasterInputs), P(RasterState), ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.ps_raster_backward.argtypes = [P(RasterDesc), P(RasterInputs), P(RasterState), ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_size_t, P(RasterGrads), ctypes.c_void_p]
+    lib.ps_camera_setup.argtypes = [ctypes.c_int32] + [ctypes.c_void_p] * 4 + [ctypes.c_int32] + \
+        [ctypes.c_void_p] * 6
+    lib.ps_camera_setup.restype = ctypes.c_int
+    lib.ps_launch_count.restype = ctypes.c_ulonglong
+    lib.ps_timing_enable.argtypes = [ctypes.c_int]
+    lib.ps_timing_enable.restype = None
+    lib.ps_timing_read.argtypes = [ctypes.POINTER(ctypes.c_float)]
+    lib.ps_timing_read.restype = ctypes.c_int
+    for f in ("ps_raster_sizes_query", "ps_raster_layout_query", "ps_raster_forward", "ps_raster_backward"):
+        getattr(lib, f).restype = ctypes.c_int
+    return lib
+
+
+lib = _load()
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc != PS_OK:
+        msg = lib.ps_last_error().decode("utf-8", "replace")
+        exc = ValueError if rc == 1 else NativeError
+        raise exc(f"{what}: {_ERR_NAMES.get(rc, rc)}: {msg}")
+
+
+def sizes(desc: RasterDesc) -> RasterSizes:
+    out = RasterSizes()
+    check(lib.ps_raster_sizes_query(ctypes.byref(desc), ctypes.byref(out)), "ps_raster_sizes_query")
+    return out
+
+
+def layout(desc: RasterDesc) -> RasterLayout:
+    out = RasterLayout()
+    check(lib.ps_raster_layout_query(ctypes.byref(desc), ctypes.byref(out)), "ps_raster_layout_query")
+    return out

@@ -1,0 +1,86 @@
+// Shared declarations of the rasterizer kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pixelsplat_b200.h"
+
+namespace ps {
+
+constexpr int kTile = PS_TILE;
+constexpr int kTilePixels = kTile * kTile;
+
+// Resolved device views of the workspace (host-built, passed by value to kernels).
+struct Geom {
+    float *depth;
+    int32_t *radii;
+    float2 *xy;
+    float4 *conic_opacity;
+    float4 *rgb;
+    ushort4 *rect;
+    uint8_t *clamped;
+    uint32_t *tile_count;
+    uint32_t *tile_start;
+    uint32_t *tile_cursor;
+    long long *n_instances;
+};
+
+struct Dims {
+    int S, V, P, M, deg, sh_layout, cov_layout, H, W, gx, gy, tiles;
+    long long capacity;
+};
+
+struct Inputs {
+    const float *means, *cov, *opac, *sh, *view, *proj, *campos, *tanfov, *bg, *scale;
+};
+
+// Per-(view,Gaussian) gradient scratch written by the composite backward.
+struct ViewGrads {
+    float2 *d_mean2d;  // NDC-scaled like upstream (x * 0.5 W, y * 0.5 H)
+    float4 *d_conic;   // x, y (half-weighted B), z, w = d_opacity
+    float4 *d_color;   // r, g, b, unused
+};
+
+void set_error(const char *fmt, ...);
+
+// Optional per-stage device timing (bench.py's roofline leg): when enabled, the entry points
+// record CUDA events on the launching stream between stages.
+enum Mark { kMarkFwdStart = 0, kMarkPreprocess, kMarkScatter, kMarkSort, kMarkCompositeFwd,
+            kMarkBwdStart, kMarkBwdZero, kMarkCompositeBwd, kMarkPreprocessBwd, kNumMarks };
+void mark(int id, cudaStream_t st);
+void count_launch();
+
+#define PS_CUDA_CHECK(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            ps::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return PS_ERR_CUDA;                                                          \
+        }                                                                                \
+    } while (0)
+
+#define PS_LAUNCH_CHECK(name)                                                            \
+    do {                                                                                 \
+        cudaError_t _e = cudaGetLastError();                                             \
+        if (_e != cudaSuccess) {                                                         \
+            ps::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));      \
+            return PS_ERR_CUDA;                                                          \
+        }                                                                                \
+        ps::count_launch();                                                              \
+    } while (0)
+
+// stage launchers (each returns PS_OK / PS_ERR_*)
+int launch_preprocess(const Dims &d, const Inputs &in, const Geom &g, cudaStream_t st);
+int launch_binning(const Dims &d, const Geom &g, unsigned long long *keys,
+                   unsigned long long *keys_alt, int sort_impl, cudaStream_t st);
+int launch_composite_forward(const Dims &d, const Inputs &in, const Geom &g,
+                             const unsigned long long *keys, float *final_T, uint32_t *n_contrib,
+                             float *out_color, cudaStream_t st);
+int launch_composite_backward(const Dims &d, const Inputs &in, const Geom &g,
+                              const unsigned long long *keys, const float *final_T,
+                              const uint32_t *n_contrib, const float *d_color, const ViewGrads &vg,
+                              cudaStream_t st);
+int launch_preprocess_backward(const Dims &d, const Inputs &in, const Geom &g, const ViewGrads &vg,
+                               const ps_raster_grads &out, cudaStream_t st);
+
+}  // namespace ps

@@ -1,0 +1,274 @@
+"""GPU parity tests of the rasterizer: CUDA path (through the C ABI) vs the CPU oracle on the same
+seeded inputs.  Bars (BASELINE.json north_star):
+  * bit-exact: depth keys, radii, tile rectangles, per-tile counts/offsets, the sorted
+    (key, Gaussian) list;  preprocess float outputs (compiled without FMA) are also bit-exact;
+  * fp32 tolerance for images: |diff| <= 2e-5 on >= 99.9 % of pixels and PSNR > 60 dB; a pixel may
+    differ more only where an alpha sits on the 1/255 or T < 1e-4 decision boundary (the GPU uses
+    ex2.approx; the oracle libm expf), bounded by 1e-2;
+  * gradients: relative max error <= 2e-3 of the largest entry (atomic summation order differs).
+"""
+import numpy as np
+import pytest
+import torch
+
+from pixelsplat_b200 import synthetic
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _native(a, bg, H, W, sort_impl=0, d_img=None, want_state=True):
+    from pixelsplat_b200.rasterizer import rasterize_gaussians
+    t = lambda x: x.to(DEV)
+    leaves = dict(means=t(a["means"])[None].clone().requires_grad_(True),
+                  cov=t(a["cov6"])[None].clone().requires_grad_(True),
+                  opac=t(a["opac"])[None].clone().requires_grad_(True))
+    use_sh = a["sh"] is not None
+    col = (a["sh"] if use_sh else a["colors"])
+    leaves["col"] = t(col)[None].clone().requires_grad_(True)
+    P = a["means"].shape[0]
+    m2d = torch.zeros(1, P, 3, device=DEV, requires_grad=True)
+    states = []
+    color, radii = rasterize_gaussians(
+        leaves["means"], leaves["cov"], leaves["opac"], leaves["col"],
+        viewmatrix=t(a["vm"])[None], projmatrix=t(a["pm"])[None], campos=t(a["campos"])[None],
+        tanfov=torch.tensor([[a["tanfovx"], a["tanfovy"]]], device=DEV),
+        background=torch.tensor([bg], dtype=torch.float32, device=DEV), image_shape=(H, W),
+        views_per_scene=1, sh_degree=a["sh_degree"], use_sh=use_sh, sort_impl=sort_impl,
+        state_out=states, means2d=m2d)
+    grads = None
+    if d_img is not None:
+        (color * torch.as_tensor(d_img, device=DEV)[None]).sum().backward()
+        grads = {k: v.grad[0].cpu().numpy() for k, v in leaves.items()}
+        grads["m2d"] = m2d.grad[0].cpu().numpy()
+    return color[0].detach().cpu().numpy(), radii[0].cpu().numpy(), states[0], grads
+
+
+def _check_forward(a, bg, H, W, sort_impl=0):
+    f = util.oracle_forward(a, bg, W, H)
+    color, radii, st, _ = _native(a, bg, H, W, sort_impl)
+    im = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in st.intermediates().items()}
+    vis = f.pre.radii > 0
+    # ---- bit-exact integer / index work
+    assert np.array_equal(radii, f.pre.radii)
+    assert np.array_equal(im["radii"][0], f.pre.radii)
+    assert np.array_equal(im["rect"][0][vis].astype(np.int32), f.pre.rect[vis])
+    assert np.array_equal(im["depth"][0][vis].view(np.uint32), f.pre.depth[vis].view(np.uint32))
+    counts = (f.binned.ranges[:, 1] - f.binned.ranges[:, 0]).astype(np.int64)
+    assert np.array_equal(im["tile_count"][0].astype(np.int64), counts)
+    assert im["num_instances"] == f.binned.keys.size
+    nz = counts > 0
+    assert np.array_equal(im["tile_start"][0][nz].astype(np.int64), f.binned.ranges[nz, 0].astype(np.int64))
+    k_up, v_up = util.upstream_keys_from_native(im["keys"], im["tile_start"][0], im["tile_count"][0])
+    assert np.array_equal(k_up, f.binned.keys), "sorted (tile|depth) keys differ"
+    assert np.array_equal(v_up, f.binned.values), "sorted Gaussian indices differ"
+    # ---- preprocess floats: IEEE-exact (no FMA on either side)
+    assert np.array_equal(im["xy"][0][vis], f.pre.xy[vis])
+    assert np.array_equal(im["conic_opacity"][0][vis], f.pre.conic_opacity[vis])
+    assert np.array_equal(im["rgb"][0][vis], f.pre.rgb[vis])
+    cl = im["clamped"][0][vis]
+    assert np.array_equal(np.stack([(cl >> c) & 1 for c in range(3)], -1), f.pre.clamped[vis])
+    # ---- composite: fp32 tolerance
+    diff = np.abs(color - f.color)
+    assert diff.max() <= 1e-2, diff.max()
+    assert (diff <= 2e-5).mean() >= 0.999, (diff <= 2e-5).mean()
+    assert util.psnr(color, f.color) > 60.0
+    assert (im["n_contrib"][0].astype(np.int64) == f.n_contrib.astype(np.int64)).mean() >= 0.999
+    assert np.abs(im["final_T"][0] - f.final_T).max() <= 1e-2
+    return f, color
+
+
+def _check_backward(a, bg, H, W, seed=1, tol=2e-3):
+    f = util.oracle_forward(a, bg, W, H)
+    d_img = np.random.default_rng(seed).standard_normal((3, H, W)).astype(np.float32)
+    b = util.oracle_backward(f, a, d_img, bg, W, H)
+    _, _, _, g = _native(a, bg, H, W, 0, d_img)
+    use_sh = a["sh"] is not None
+    errs = dict(means=util.rel_err(g["means"], b.dL_dmeans), cov=util.rel_err(g["cov"], b.dL_dcov6),
+                opac=util.rel_err(g["opac"], b.dL_dopacity),
+                col=util.rel_err(g["col"], b.dL_dsh if use_sh else b.dL_dcolors),
+                m2d=util.rel_err(g["m2d"][:, :2], b.dL_dmean2D))
+    assert np.all(g["m2d"][:, 2] == 0)
+    for k, e in errs.items():
+        assert e <= tol, (k, errs)
+    return errs
+
+
+@pytest.mark.parametrize("sort_impl", [0, 1])
+def test_config0_forward(sort_impl):
+    """BASELINE configs[0]: 64x64, 1k random Gaussians, 1 view."""
+    sc = synthetic.scene_random_frustum(seed=0)
+    _check_forward(util.view_args(sc), (0.0, 0.0, 0.0), *sc.image_shape, sort_impl=sort_impl)
+
+
+def test_config0_backward_nonzero_background():
+    sc = synthetic.scene_random_frustum(seed=3)
+    _check_backward(util.view_args(sc), (0.1, 0.2, 0.3), *sc.image_shape)
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_lower_sh_degrees(deg):
+    sc = synthetic.scene_random_frustum(seed=4, sh_degree=deg)
+    a = util.view_args(sc)
+    _check_forward(a, (0.0, 0.0, 0.0), *sc.image_shape)
+    _check_backward(a, (0.0, 0.0, 0.0), *sc.image_shape)
+
+
+def test_colors_precomp_path():
+    sc = synthetic.scene_random_frustum(seed=5, sh_degree=0)
+    a = util.view_args(sc, use_sh=False)
+    _check_forward(a, (0.2, 0.0, 0.1), *sc.image_shape)
+    _check_backward(a, (0.2, 0.0, 0.1), *sc.image_shape)
+
+
+def test_ragged_image_size_and_dense_stack():
+    """70x50 (partial tiles) with 4k opaque Gaussians: exercises early termination."""
+    sc = synthetic.scene_random_frustum(seed=6, image_hw=(50, 70), num_gaussians=4000, z_range=(1.0, 4.0))
+    a = util.view_args(sc)
+    f, _ = _check_forward(a, (0.0, 0.0, 0.0), 50, 70)
+    assert (f.final_T < 1e-3).mean() > 0.05, "scene should saturate some pixels"
+    _check_backward(a, (0.0, 0.0, 0.0), 50, 70)
+
+
+def test_long_tiles_use_every_sort_path():
+    """One 16x16 image, 30k Gaussians on it: the single tile exceeds the shared-memory sort
+    capacities (2048 / 12288) and takes the global ping-pong path."""
+    sc = synthetic.scene_random_frustum(seed=7, image_hw=(16, 16), num_gaussians=30000, z_range=(2.0, 30.0))
+    a = util.view_args(sc)
+    f, _ = _check_forward(a, (0.0, 0.0, 0.0), 16, 16)
+    assert f.binned.keys.size > 12288
+    sc = synthetic.scene_random_frustum(seed=8, image_hw=(32, 32), num_gaussians=14000, z_range=(2.0, 30.0))
+    f, _ = _check_forward(util.view_args(sc), (0.0, 0.0, 0.0), 32, 32)
+    cnt = f.binned.ranges[:, 1] - f.binned.ranges[:, 0]
+    assert cnt.max() > 2048
+
+
+def test_empty_and_single():
+    """Nothing visible (all behind the camera) and a single Gaussian."""
+    sc = synthetic.scene_random_frustum(seed=9, num_gaussians=64)
+    sc.means[:, 2] = -sc.means[:, 2]
+    a = util.view_args(sc)
+    f, color = _check_forward(a, (0.3, 0.4, 0.5), *sc.image_shape)
+    assert f.binned.keys.size == 0
+    assert np.allclose(color, np.array([0.3, 0.4, 0.5], np.float32)[:, None, None])
+    d_img = np.ones((3, 64, 64), np.float32)
+    _, _, _, g = _native(a, (0.3, 0.4, 0.5), 64, 64, 0, d_img)
+    assert all(np.all(v == 0) for v in g.values())
+    sc1 = synthetic.scene_random_frustum(seed=10, num_gaussians=1)
+    sc1.means[0] = torch.tensor([0.0, 0.0, 3.0])
+    _check_forward(util.view_args(sc1), (0.0, 0.0, 0.0), *sc1.image_shape)
+    _check_backward(util.view_args(sc1), (0.0, 0.0, 0.0), *sc1.image_shape)
+
+
+def test_capacity_overflow_reruns():
+    from pixelsplat_b200 import rasterizer
+    sc = synthetic.scene_random_frustum(seed=11, num_gaussians=3000)
+    a = util.view_args(sc)
+    H, W = sc.image_shape
+    rasterizer._capacity_hint[(0, 1, 1, 3000, H, W)] = 16   # far too small
+    _check_forward(a, (0.0, 0.0, 0.0), H, W)
+    assert rasterizer._capacity_hint[(0, 1, 1, 3000, H, W)] > 16
+
+
+def test_config1_full_size():
+    """BASELINE configs[1]: 2 context views -> 1 target, 256x256, 3 Gaussians/pixel (P = 393 216)."""
+    sc = synthetic.scene_re10k_like(seed=0)
+    a = util.view_args(sc)
+    f, color = _check_forward(a, (0.0, 0.0, 0.0), 256, 256)
+    print("config1: N =", f.binned.keys.size, "visible =", int((f.pre.radii > 0).sum()))
+    _check_backward(a, (0.0, 0.0, 0.0), 256, 256)
+
+
+def test_config4_high_res_tile_stress():
+    """BASELINE configs[4] (one scene of it): 3 context views, 512x512 target, P = 2 359 296."""
+    sc = synthetic.scene_re10k_like(seed=1, image_hw=(512, 512), context_views=3)
+    a = util.view_args(sc)
+    f, _ = _check_forward(a, (0.0, 0.0, 0.0), 512, 512)
+    print("config4: N =", f.binned.keys.size)
+
+
+def test_render_cuda_api_matches_oracle():
+    """Through the reference-facing Python API (render_cuda signature, native layouts, fused
+    scale-invariant rescale, on-device camera set-up): tolerance only, since the matrices are
+    computed on the device."""
+    from pixelsplat_b200.decoder import render_cuda
+    sc = synthetic.scene_re10k_like(seed=2, image_hw=(128, 128))
+    t = lambda x: x.to(DEV)
+    img = render_cuda(t(sc.extrinsics), t(sc.intrinsics), t(sc.near), t(sc.far), sc.image_shape,
+                      t(sc.background)[None], t(sc.means)[None], t(sc.covariances)[None],
+                      t(sc.harmonics)[None], t(sc.opacities)[None])
+    f = util.oracle_forward(util.view_args(sc), (0.0, 0.0, 0.0), 128, 128)
+    got = img[0].cpu().numpy()
+    assert util.psnr(got, f.color) > 50.0
+    assert (np.abs(got - f.color) <= 1e-4).mean() > 0.995
+
+
+def test_shared_gaussians_multi_view_and_gradient_sum():
+    """S=2 scenes x V=3 views in one call == six single-view calls; gradients sum over views."""
+    from pixelsplat_b200.decoder import render_views
+    scs = [synthetic.scene_re10k_like(seed=20 + i, image_hw=(64, 64), target_views=3) for i in range(2)]
+    t = lambda x: x.to(DEV)
+    st = lambda name: torch.stack([t(getattr(s, name)) for s in scs])
+    leaves = [st("means").requires_grad_(True), st("covariances").requires_grad_(True),
+              st("harmonics").requires_grad_(True), st("opacities").requires_grad_(True)]
+    bg = torch.zeros(2, 3, 3, device=DEV)
+    out = render_views(st("extrinsics"), st("intrinsics"), st("near"), st("far"), (64, 64), bg, *leaves)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    g_batched = [l.grad.clone() for l in leaves]
+    for l in leaves:
+        l.grad = None
+    total = 0
+    for s in range(2):
+        for v in range(3):
+            o = render_views(st("extrinsics")[s:s + 1, v:v + 1], st("intrinsics")[s:s + 1, v:v + 1],
+                             st("near")[s:s + 1, v:v + 1], st("far")[s:s + 1, v:v + 1], (64, 64),
+                             bg[s:s + 1, v:v + 1], *[l[s:s + 1] for l in leaves])
+            assert torch.allclose(o[0, 0], out[s, v], atol=1e-6)
+            total = total + (o[0, 0] * w[s, v]).sum()
+    total.backward()
+    for gb, l in zip(g_batched, leaves):
+        assert util.rel_err(gb.cpu().numpy(), l.grad.cpu().numpy()) < 1e-3
+
+
+def test_gaussian_rasterizer_dropin_surface():
+    """The extension classes the reference imports (cuda_splatting.py:5-8): argument checks and a
+    render through them."""
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    sc = synthetic.scene_random_frustum(seed=12)
+    a = util.view_args(sc)
+    t = lambda x: x.to(DEV)
+    H, W = sc.image_shape
+    settings = GaussianRasterizationSettings(
+        image_height=H, image_width=W, tanfovx=a["tanfovx"], tanfovy=a["tanfovy"],
+        bg=torch.zeros(3, device=DEV), scale_modifier=1.0, viewmatrix=t(a["vm"]).reshape(4, 4),
+        projmatrix=t(a["pm"]).reshape(4, 4), sh_degree=a["sh_degree"], campos=t(a["campos"]),
+        prefiltered=False, debug=False)
+    r = GaussianRasterizer(settings)
+    m2d = torch.zeros_like(t(a["means"]), requires_grad=True)
+    img, radii = r(means3D=t(a["means"]), means2D=m2d, shs=t(a["sh"]), colors_precomp=None,
+                   opacities=t(a["opac"])[:, None], cov3D_precomp=t(a["cov6"]))
+    f = util.oracle_forward(a, (0, 0, 0), W, H)
+    assert img.shape == (3, H, W) and radii.dtype == torch.int32
+    assert util.psnr(img.detach().cpu().numpy(), f.color) > 60
+    img.sum().backward()
+    assert m2d.grad is not None and m2d.grad.shape == m2d.shape
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(means3D=t(a["means"]), means2D=m2d, opacities=t(a["opac"])[:, None], cov3D_precomp=t(a["cov6"]))
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=t(a["means"]), means2D=m2d, shs=t(a["sh"]), opacities=t(a["opac"])[:, None])
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        r(means3D=a["means"], means2D=None, shs=a["sh"], opacities=a["opac"][:, None], cov3D_precomp=a["cov6"])
+
+
+def test_idempotent_and_deterministic_forward():
+    """Size-independent property: the forward (including the atomic scatter + sort) is
+    bit-reproducible run to run."""
+    sc = synthetic.scene_re10k_like(seed=5, image_hw=(128, 128))
+    a = util.view_args(sc)
+    c1, r1, s1, _ = _native(a, (0, 0, 0), 128, 128)
+    c2, r2, s2, _ = _native(a, (0, 0, 0), 128, 128)
+    assert np.array_equal(c1, c2) and np.array_equal(r1, r2)
+    assert torch.equal(s1.intermediates()["keys"], s2.intermediates()["keys"])
