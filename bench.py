@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- rendered views/sec, rasterizer forward+backward @256x256, 3 Gaussians/pixel.
+
+Workload = BASELINE.json configs[1]: 2 context views -> 1 target view, 256x256, P = 393 216
+Gaussians, SH degree 4, synthetic re10k-like scenes (pixelsplat_b200/synthetic.py).  A "step" is
+one forward + backward of the rasterizer hot path over one batch of `--views` target views of one
+scene (default 1, exactly configs[1]).
+
+  value     : whole-job views/s, inputs resident in HBM, K steps back to back between two CUDA
+              events (a pool of scenes larger than L2 is cycled, so no step re-reads a hot L2).
+  e2e       : same metric through the reference-facing `render_cuda` call with HOST (pinned)
+              buffers: per step H2D of every input, forward, backward, D2H of the image and of a
+              gradient checksum -- all inside the timed region.
+  roofline  : the dominant kernel (found live with the library's per-stage CUDA events).
+  cpu_baseline : the pure-PyTorch CPU oracle (oracle/raster_torch.py, kind "port") on one view.
+  --impl reference : the reference arm.  The reference's own rasterizer is an un-vendored CUDA
+              dependency that cannot be installed offline, so this arm times the CPU restatement
+              (the "pure-PyTorch CPU composite" BASELINE.json names), kind "port".
+
+Multi-GPU: replicas only (the rasterizer has no trainable parameters, so there is no gradient
+all-reduce on this path); ranks render disjoint scenes, time is the max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "rendered views/sec fwd+bwd @256x256, 3 gauss/px"
+UNIT = "views/s"
+IMAGE = (256, 256)
+STAGES = ["preprocess", "count_scan_scatter", "tile_sort", "composite_fwd", "grad_zero_fill",
+          "composite_bwd", "preprocess_bwd"]
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_scene(seed: int, views: int):
+    from pixelsplat_b200 import synthetic
+    return synthetic.scene_re10k_like(seed=seed, image_hw=IMAGE, context_views=2,
+                                      gaussians_per_pixel=3, sh_degree=4, target_views=views)
+
+
+def scene_host_tensors(sc, pin: bool):
+    t = dict(extrinsics=sc.extrinsics, intrinsics=sc.intrinsics, near=sc.near, far=sc.far,
+             means=sc.means[None], covariances=sc.covariances[None], harmonics=sc.harmonics[None],
+             opacities=sc.opacities[None])
+    t = {k: v.contiguous().float() for k, v in t.items()}
+    return {k: (v.pin_memory() if pin else v) for k, v in t.items()}
+
+
+GAUSS_KEYS = ("means", "covariances", "harmonics", "opacities")
+
+
+def render_step(d, d_img, views):
+    """One forward + backward of the hot path through the public API; returns (image, grads)."""
+    from pixelsplat_b200.decoder import render_views
+    leaves = [d[k] for k in GAUSS_KEYS]
+    bg = torch.zeros((1, views, 3), device=d["means"].device)
+    img = render_views(d["extrinsics"][None], d["intrinsics"][None], d["near"][None], d["far"][None],
+                       IMAGE, bg, *leaves)
+    grads = torch.autograd.grad(img, leaves, d_img)
+    return img, grads
+
+
+def algorithmic_bytes(P, M, N, vis, HW, cov_floats=9):
+    """Per-view algorithmic HBM bytes of each stage."""
+    return {
+        "preprocess": P * (12 + 4 * cov_floats + 4 + 4) + vis * (12 * M + 4 + 8 + 16 + 16 + 8 + 1),
+        "count_scan_scatter": P * 4 + vis * (8 + 4) + N * 8,
+        "tile_sort": N * 16,
+        "composite_fwd": N * (8 + 8 + 16 + 16) + HW * 20,
+        "grad_zero_fill": P * 40,
+        "composite_bwd": N * (8 + 8 + 16 + 16) + N * 36 + HW * 20,
+        "preprocess_bwd": P * (12 + 4 * cov_floats + 4) + vis * (40 + 12 * M) +
+                          P * (12 + 4 * cov_floats + 4 + 12 * M),
+    }
+
+
+def cpu_baseline_sample(threads: int, seed: int = 0):
+    """The pure-PyTorch CPU oracle, forward + backward of ONE configs[1] view."""
+    from oracle import raster_torch as rt
+    torch.set_num_threads(threads)
+    sc = make_scene(seed, 1)
+    a = rt.prepare_view(sc.means, sc.covariances, sc.harmonics, sc.opacities, sc.extrinsics[0],
+                        sc.intrinsics[0], sc.near[0], sc.far[0])
+    leaves = {k: a[k].clone().requires_grad_(True) for k in ("means", "cov6", "opac", "sh")}
+    g = torch.Generator().manual_seed(1)
+    d_img = torch.randn(3, *IMAGE, generator=g)
+    t0 = time.perf_counter()
+    color, _ = rt.rasterize(leaves["means"], leaves["cov6"], leaves["opac"], leaves["sh"], None,
+                            a["vm"], a["pm"], a["campos"], a["tanfovx"], a["tanfovy"], torch.zeros(3),
+                            IMAGE[1], IMAGE[0], a["sh_degree"])
+    (color * d_img).sum().backward()
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt = cpu_baseline_sample(threads, seed=i)
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = len(times) / total
+    sample = (f"{len(times)} timed steps, each 1 view of configs[1] (256x256, P=393216), fwd+bwd, "
+              f"pure-PyTorch CPU oracle (oracle/raster_torch.py)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: re10k-like 2-view -> 1 target, 256x256, 3 gauss/px, "
+                               "batch 1, rasterizer fwd+bwd", "views_per_step": 1},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference's CUDA rasterizer (diff-gaussian-rasterization-modified) is an "
+                "un-vendored dependency that cannot be installed offline; this arm is the CPU "
+                "restatement (kind=port), not the reference's CUDA path",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--views", type=int, default=1, help="target views per step (one scene)")
+    ap.add_argument("--pool", type=int, default=4, help="distinct scenes cycled (> L2 in total)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if args.steps == 100 and args.warmup == 10:
+            args.steps, args.warmup = 2, 1
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: pixelsplat_b200 has no CPU path "
+                         "(use --impl reference for the CPU arm)")
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from pixelsplat_b200 import _lib, rasterizer
+    from pixelsplat_b200.decoder import render_views  # noqa: F401  (loads the CUDA library)
+
+    K, W_, V = args.steps, args.warmup, args.views
+    pool_host = [scene_host_tensors(make_scene(1000 * rank + i, V), pin=True) for i in range(args.pool)]
+    P = pool_host[0]["means"].shape[1]
+    pool_dev = []
+    for h in pool_host:
+        d = {k: v.to(dev) for k, v in h.items()}
+        for k in GAUSS_KEYS:
+            d[k].requires_grad_(True)
+        pool_dev.append(d)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    d_img = torch.randn((1, V, 3, *IMAGE), generator=g).to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: device-resident inputs, K steps back to back
+    rasterizer.set_capacity_check("sync")
+    for i in range(W_):
+        render_step(pool_dev[i % args.pool], d_img, V)
+    rasterizer.set_capacity_check("deferred")   # capacity known from warm-up; verified at backward
+    for i in range(W_):
+        render_step(pool_dev[i % args.pool], d_img, V)
+    barrier()
+    launches0 = _lib.lib.ps_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        e0.record()
+        for i in range(K):
+            render_step(pool_dev[i % args.pool], d_img, V)
+        e1.record()
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = _lib.lib.ps_launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = world * K * V / (ms_total * 1e-3)
+
+    # ---------------- e2e: host buffers, H2D + fwd + bwd + D2H per step, prefetch on a side stream
+    e2e = None
+    if not args.no_e2e:
+        copy_stream = torch.cuda.Stream(dev)
+        img_host = torch.empty((1, V, 3, *IMAGE), dtype=torch.float32).pin_memory()
+        chk_host = torch.empty((1,), dtype=torch.float32).pin_memory()
+        h2d_bytes = sum(v.numel() * 4 for v in pool_host[0].values())
+        d2h_bytes = img_host.numel() * 4 + 4
+
+        def upload(h):
+            with torch.cuda.stream(copy_stream):
+                d = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return d, ev
+
+        def e2e_loop(n):
+            nxt = upload(pool_host[0])
+            for i in range(n):
+                d, ev = nxt
+                if i + 1 < n:
+                    nxt = upload(pool_host[(i + 1) % args.pool])
+                torch.cuda.current_stream().wait_event(ev)
+                for k in GAUSS_KEYS:
+                    d[k].requires_grad_(True)
+                    d[k].record_stream(torch.cuda.current_stream())
+                img, grads = render_step(d, d_img, V)
+                img_host.copy_(img.detach(), non_blocking=True)
+                chk_host.copy_(sum(gr.sum() for gr in grads).reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        e2e_loop(W_)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_loop(K)
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * K * V / dt, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": d2h_bytes,
+               "how": "render_views(...) public API on pinned host inputs; H2D prefetched on a side "
+                      "stream, image + gradient checksum read back every step; wall clock, max over ranks"}
+
+    # ---------------- roofline: per-stage CUDA events inside the library
+    roofline, stage_ms, stats = None, None, None
+    if rank == 0:
+        rasterizer.set_capacity_check("sync")
+        _lib.lib.ps_timing_enable(1)
+        acc = [0.0] * 7
+        buf = (ctypes.c_float * 7)()
+        n_prof = min(K, 20)
+        states = []
+        for i in range(n_prof):
+            render_step(pool_dev[i % args.pool], d_img, V)
+            _lib.check(_lib.lib.ps_timing_read(buf), "ps_timing_read")
+            for j in range(7):
+                acc[j] += buf[j]
+        _lib.lib.ps_timing_enable(0)
+        stage_ms = {s: acc[j] / n_prof for j, s in enumerate(STAGES)}
+        # workload statistics (N, visible) from one more forward
+        from pixelsplat_b200.decoder import render_views as rv
+        d = pool_dev[0]
+        rv(d["extrinsics"][None], d["intrinsics"][None], d["near"][None], d["far"][None], IMAGE,
+           torch.zeros((1, V, 3), device=dev), *[d[k] for k in GAUSS_KEYS], state_out=states)
+        im = states[0].intermediates()
+        N = im["num_instances"] / V
+        vis = float((im["radii"] > 0).sum().item()) / V
+        stats = {"instances_per_view": N, "visible_per_view": vis, "gaussians": P}
+        ab = algorithmic_bytes(P, 25, N, vis, IMAGE[0] * IMAGE[1])
+        dom = max(stage_ms, key=stage_ms.get)
+        pk, pk_kind = peaks()
+        achieved = V * ab[dom] / (stage_ms[dom] * 1e-3) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
+                    "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
+                    "peak_source": f"{pk_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                    "algorithmic_bytes_per_launch": V * ab[dom], "avg_launch_ms": stage_ms[dom],
+                    "pair_evals_per_s": (V * N * 256 / (stage_ms[dom] * 1e-3)
+                                         if dom.startswith("composite") else None),
+                    "all_stages_gbs": {s: V * ab[s] / (stage_ms[s] * 1e-3) / 1e9 for s in STAGES
+                                       if stage_ms[s] > 0}}
+    torch.cuda.synchronize()
+
+    # ---------------- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        dt = cpu_baseline_sample(threads)
+        cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "1 view of configs[1] (256x256, P=393216) forward+backward, pure-PyTorch CPU "
+                         f"oracle (oracle/raster_torch.py), torch.set_num_threads({threads}), {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: re10k-like 2-view -> 1 target, 256x256, 3 gauss/px, "
+                                   "batch 1, rasterizer fwd+bwd (SH degree 4)",
+                       "views_per_step": V, "gaussians": P, "parallelism": f"replicas x{world}",
+                       "l2": f"pool of {args.pool} scenes ({args.pool * 140} MB of inputs) cycled: "
+                             "inputs larger than L2, no flush",
+                       "capacity_check": "deferred (verified at backward)"},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "stage_ms": stage_ms, "workload_stats": stats,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

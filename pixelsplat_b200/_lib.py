@@ -10,7 +10,7 @@ import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "_C" / "libpixelsplat_b200.so"
+LIB_PATH = Path(os.environ.get("PIXELSPLAT_B200_LIB", _PKG / "_C" / "libpixelsplat_b200.so"))
 
 PS_OK = 0
 PS_SH_M3, PS_SH_3M = 0, 1

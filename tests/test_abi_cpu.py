@@ -1,0 +1,108 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/*.h declares,
+its structs agree with the ctypes mirrors, argument validation works without a GPU, and the
+product path fails loudly (no fallback) when the library or the device is missing."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+HEADER = ROOT / "include" / "pixelsplat_b200.h"
+
+
+def declared_functions():
+    text = HEADER.read_text()
+    return sorted(set(re.findall(r"PS_API\s+[\w\s\*]+?\b(ps_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pixelsplat_b200 import _lib
+    names = declared_functions()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(_lib.lib, n), f"{n} declared in the header but not exported"
+    assert set(_lib.EXPORTS) == set(names)
+    assert _lib.lib.ps_version() >= 100
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """Compile a C probe against the header with gcc and compare sizeof/offsetof."""
+    from pixelsplat_b200 import _lib
+    probe = tmp_path / "probe.c"
+    probe.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pixelsplat_b200.h"\n'
+                     "int main(void){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu\\n\","
+                     "sizeof(ps_raster_desc),offsetof(ps_raster_desc,instance_capacity),"
+                     "sizeof(ps_raster_inputs),sizeof(ps_raster_state),sizeof(ps_raster_sizes),"
+                     "sizeof(ps_raster_layout),sizeof(ps_raster_grads),offsetof(ps_raster_desc,sort_impl));return 0;}\n")
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", str(HEADER.parent), str(probe), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(_lib.RasterDesc), _lib.RasterDesc.instance_capacity.offset,
+            ctypes.sizeof(_lib.RasterInputs), ctypes.sizeof(_lib.RasterState),
+            ctypes.sizeof(_lib.RasterSizes), ctypes.sizeof(_lib.RasterLayout),
+            ctypes.sizeof(_lib.RasterGrads), _lib.RasterDesc.sort_impl.offset]
+    assert got == want
+
+
+def test_sizes_layout_and_validation_without_gpu():
+    from pixelsplat_b200 import _lib
+    d = _lib.RasterDesc(2, 3, 1000, 25, 4, _lib.PS_SH_3M, _lib.PS_COV_3X3, 70, 50, 0, 12345)
+    s, lay = _lib.sizes(d), _lib.layout(d)
+    vp, tiles = 2 * 3 * 1000, 4 * 5
+    assert lay.depth == 0 and lay.radii >= vp * 4 and lay.keys == 0 and lay.keys_alt >= 12345 * 8
+    assert s.binning_bytes >= 2 * 12345 * 8 and s.image_bytes >= 2 * 6 * 70 * 50 * 4
+    assert s.backward_bytes >= vp * 40
+    offs = [getattr(lay, f) for f, _ in _lib.RasterLayout._fields_[:11]]
+    assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
+    assert lay.tile_start - lay.tile_count >= 6 * tiles * 4
+    for field, bad in (("n_gaussians", 0), ("sh_degree", 5), ("sh_coeffs", 26), ("sh_layout", 7),
+                       ("cov_layout", -1), ("height", 0), ("instance_capacity", 0),
+                       ("instance_capacity", 1 << 31)):
+        d2 = _lib.RasterDesc(1, 1, 10, 25, 4, 0, 0, 16, 16, 0, 100)
+        setattr(d2, field, bad)
+        with pytest.raises(ValueError, match="PS_ERR_INVALID_ARGUMENT"):
+            _lib.sizes(d2)
+    d3 = _lib.RasterDesc(1, 1, 10, 4, 2, 0, 0, 16, 16, 0, 100)    # degree 2 needs 9 coefficients
+    with pytest.raises(ValueError, match="needs 9 coefficients"):
+        _lib.sizes(d3)
+    # NULL pointers are rejected before anything is launched
+    d4 = _lib.RasterDesc(1, 1, 10, 25, 4, 0, 0, 16, 16, 0, 100)
+    rc = _lib.lib.ps_raster_forward(ctypes.byref(d4), None, None, None, None, None, None)
+    assert rc == 1 and b"NULL" in _lib.lib.ps_last_error()
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are rejected; a missing library is an ImportError, not a silent fallback."""
+    from pixelsplat_b200.rasterizer import rasterize_gaussians
+    P = 8
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        rasterize_gaussians(torch.zeros(1, P, 3), torch.zeros(1, P, 6), torch.zeros(1, P),
+                            torch.zeros(1, P, 25, 3), viewmatrix=torch.zeros(1, 16),
+                            projmatrix=torch.zeros(1, 16), campos=torch.zeros(1, 3),
+                            tanfov=torch.ones(1, 2), background=torch.zeros(1, 3), image_shape=(16, 16),
+                            views_per_scene=1, sh_degree=4)
+    env = dict(os.environ, PIXELSPLAT_B200_LIB="/nonexistent/libpixelsplat_b200.so")
+    r = subprocess.run([sys.executable, "-c", "import pixelsplat_b200.rasterizer"], cwd=str(ROOT), env=env,
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_product_never_imports_the_oracle():
+    for path in (ROOT / "pixelsplat_b200").rglob("*"):
+        if path.suffix in (".py", ".cu", ".cuh", ".h"):
+            assert "oracle" not in path.read_text().replace("checked bit-for-bit against oracle/", ""), path
+
+
+def test_synthetic_scenes_are_deterministic():
+    from pixelsplat_b200 import synthetic
+    a, b = synthetic.scene_re10k_like(seed=3, image_hw=(32, 32)), synthetic.scene_re10k_like(seed=3, image_hw=(32, 32))
+    assert torch.equal(a.means, b.means) and torch.equal(a.harmonics, b.harmonics)
+    assert a.num_gaussians == 2 * 32 * 32 * 3 and a.harmonics.shape[-2:] == (3, 25)
+    assert abs(float(synthetic.scene_re10k_like(seed=0).near[0]) - 0.2933) < 1e-3
+    evals = torch.linalg.eigvalsh(a.covariances)
+    assert (evals > 0).all()
