@@ -143,6 +143,13 @@ def algorithmic_bytes(P, M, N, vis, HW, cov_floats=9):
     }
 
 
+def cpu_threads() -> int:
+    """Threads used for the CPU arm: the oracle's per-tile tensors are small (256 x ~1.5k), and
+    on a 128-core host torch's intra-op pool over-subscribes badly (measured: 325 s per view with
+    128 threads vs 9 s with 8), so the pool is capped at 8."""
+    return min(os.cpu_count() or 1, 8)
+
+
 def cpu_baseline_sample(threads: int, seed: int = 0):
     """The pure-PyTorch CPU oracle, forward + backward of ONE configs[1] view."""
     from oracle import raster_torch as rt
@@ -164,7 +171,7 @@ def cpu_baseline_sample(threads: int, seed: int = 0):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = cpu_threads()
     times = []
     for i in range(args.warmup + args.steps):
         dt = cpu_baseline_sample(threads, seed=i)
@@ -194,7 +201,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--views", type=int, default=1, help="target views per step (one scene)")
@@ -206,7 +213,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        if args.steps == 100 and args.warmup == 10:
+        if args.steps == 400 and args.warmup == 10:
             args.steps, args.warmup = 2, 1
         run_reference(args, rank, world)
         return
@@ -354,7 +361,7 @@ def main():
     # ---------------- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = cpu_threads()
         dt = cpu_baseline_sample(threads)
         cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "1 view of configs[1] (256x256, P=393216) forward+backward, pure-PyTorch CPU "

@@ -61,6 +61,9 @@ typedef struct ps_raster_desc {
     int32_t cov_layout;      /* PS_COV_*                                                       */
     int32_t height, width;   /* image size in pixels                                           */
     int32_t sort_impl;       /* 0 = native per-tile radix sort; 1 = CUB segmented sort (debug)  */
+    int32_t sort_segment_hint; /* longest (view,tile) list expected (from a previous call's
+                                  n_instances_host[1]); 0 = unknown.  Only selects the shared-memory
+                                  size of the sort; any value is correct                        */
     int64_t instance_capacity; /* room, in (tile,Gaussian) instances, summed over all S*V views */
 } ps_raster_desc;
 
@@ -105,7 +108,7 @@ typedef struct ps_raster_layout {
     size_t tile_count;    /* u32  [S*V*tiles]                                                  */
     size_t tile_start;    /* u32  [S*V*tiles] exclusive scan, global instance offsets          */
     size_t tile_cursor;   /* u32  scratch                                                      */
-    size_t n_instances;   /* i64  [1] total instances needed (may exceed capacity)             */
+    size_t n_instances;   /* i64  [2] total instances needed (may exceed capacity), longest segment */
     /* binning */
     size_t keys;          /* u64  [capacity]  per tile sorted (float_bits(depth)<<32 | gaussian) */
     size_t keys_alt;      /* u64  [capacity]  scratch                                          */
@@ -156,8 +159,8 @@ PS_API int ps_camera_setup(int32_t n_views, const float *extrinsics, const float
  * Replaces _C.rasterize_gaussians for S*V views at once.
  *   out_color      [S*V, 3, H, W]
  *   out_radii      [S*V, P] int32 or NULL
- *   n_instances_host  pinned HOST int64 or NULL: receives the instance count asynchronously
- *                  (valid once `stream` reaches this point).  If it exceeds
+ *   n_instances_host  pinned HOST int64[2] or NULL: receives {instance count, longest (view,tile)
+ *                  list} asynchronously (valid once `stream` reaches this point).  If the count exceeds
  *                  desc->instance_capacity the binning was truncated and out_color is INVALID:
  *                  the caller must re-run with a larger capacity (pixelsplat_b200.rasterizer does).
  */
@@ -174,6 +177,61 @@ PS_API int ps_raster_backward(const ps_raster_desc *desc, const ps_raster_inputs
                        const ps_raster_state *state, const float *d_color /* [S*V,3,H,W] */,
                        void *scratch, size_t scratch_bytes, const ps_raster_grads *grads,
                        void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Epipolar sampled cross-attention.
+ * Replaces, inside EpipolarTransformer.forward
+ * (/root/reference/src/model/encoder/epipolar/epipolar_transformer.py:96-142):
+ *   ps_epipolar_geometry            EpipolarSampler's ray generation + project_rays
+ *                                   (epipolar_sampler.py:62-88, geometry/epipolar_lines.py:157-251),
+ *                                   get_depth (epipolar_lines.py:264-292, projection.py:176-230),
+ *                                   depth clip + depth_to_relative_disparity
+ *                                   (epipolar_transformer.py:103-119, conversions.py:17-27);
+ *   ps_epipolar_attention_forward / _backward
+ *                                   F.grid_sample of the samples (epipolar_sampler.py:98-111), the
+ *                                   depth positional encoding (epipolar_transformer.py:120-121,
+ *                                   positional_encoding.py:28-33) and Attention.forward with z != None
+ *                                   (transformer/attention.py:54-70) for one transformer layer.
+ * Ray index r = row * grid_w + col over the (down-scaled) feature grid; "other view" ov of view v
+ * is view ov if ov < v else ov + 1 (misc/heterogeneous_pairings.py:9-24).
+ */
+typedef struct ps_epipolar_desc {
+    int32_t batch, views;     /* b, v (v >= 2)                                                  */
+    int32_t grid_h, grid_w;   /* ray / feature grid                                             */
+    int32_t samples;          /* S <= 32 samples per epipolar segment                           */
+    int32_t channels;         /* feature channels, must be 128                                  */
+    int32_t heads;            /* 1..4                                                           */
+    int32_t pe_dim;           /* 2 * num_octaves of the depth encoding (<= 32, heads*pe_dim<=96) */
+} ps_epipolar_desc;
+
+typedef struct ps_epipolar_inputs {
+    const float *features;      /* [b, v, grid_h, grid_w, 128] channels-last                    */
+    const float *segments;      /* [b, v, v-1, R, 4] xy_min.xy, xy_max.xy (from ps_epipolar_geometry) */
+    const uint8_t *valid;       /* [b, v, v-1, R]                                               */
+    const float *rel_disparity; /* [b, v, v-1, R, S]                                            */
+    const float *q_feat;        /* [b*v*R, heads, 128]  scale * W_k,h^T q_h                     */
+    const float *q_pe;          /* [b*v*R, heads, pe_dim]  W_d^T of the above                   */
+    const float *bias;          /* [b*v*R, heads, v-1] or NULL (view-embedding score term)      */
+} ps_epipolar_inputs;
+
+/* segments/valid/rel_disparity as above; t_range [b, v, v-1, R, 2] (t_min, t_max) or NULL. */
+PS_API int ps_epipolar_geometry(int32_t batch, int32_t views, int32_t grid_h, int32_t grid_w,
+                                int32_t samples, const float *extrinsics /* [b,v,4,4] c2w */,
+                                const float *intrinsics /* [b,v,3,3] */, const float *near_plane,
+                                const float *far_plane /* [b,v] */, float *segments, uint8_t *valid,
+                                float *rel_disparity, float *t_range, void *stream);
+
+/* z [N,heads,128] = sum_s a_s f_s;  e [N,heads,pe_dim] = sum_s a_s PE(rd_s);
+ * mass [N,heads,v-1] = per-other-view attention mass (or NULL);  lse [N,heads] log-sum-exp. */
+PS_API int ps_epipolar_attention_forward(const ps_epipolar_desc *desc, const ps_epipolar_inputs *in,
+                                         float *z, float *e, float *mass, float *lse, void *stream);
+
+/* d_row [N,heads] = dz.z + de.e (+ dmass.mass).  dfeatures [b,v,grid_h,grid_w,128] must be
+ * zero-initialised by the caller; the kernel accumulates into it atomically. */
+PS_API int ps_epipolar_attention_backward(const ps_epipolar_desc *desc, const ps_epipolar_inputs *in,
+                                          const float *lse, const float *dz, const float *de,
+                                          const float *dmass, const float *d_row, float *dq_feat,
+                                          float *dq_pe, float *dbias, float *dfeatures, void *stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,8 @@ class RasterDesc(ctypes.Structure):
         ("n_gaussians", ctypes.c_int32), ("sh_coeffs", ctypes.c_int32),
         ("sh_degree", ctypes.c_int32), ("sh_layout", ctypes.c_int32),
         ("cov_layout", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
-        ("sort_impl", ctypes.c_int32), ("instance_capacity", ctypes.c_int64),
+        ("sort_impl", ctypes.c_int32), ("sort_segment_hint", ctypes.c_int32),
+        ("instance_capacity", ctypes.c_int64),
     ]
 
 

@@ -99,7 +99,7 @@ static Layout make_layout(const ps_raster_desc *d) {
     L.off.tile_count = take(vt * 4);
     L.off.tile_start = take(vt * 4);
     L.off.tile_cursor = take(vt * 4);
-    L.off.n_instances = take(8);
+    L.off.n_instances = take(16);   // [0] total instances, [1] longest segment
     L.sizes.geom_bytes = o;
     o = 0;
     L.off.keys = take((size_t)m.capacity * 8);
@@ -226,10 +226,10 @@ PS_API int ps_raster_forward(const ps_raster_desc *desc, const ps_raster_inputs 
     mark(kMarkFwdStart, st);
     if ((rc = launch_preprocess(d, I, g, st))) return rc;
     mark(kMarkPreprocess, st);
-    if ((rc = launch_binning(d, g, keys, keys_alt, desc->sort_impl, st))) return rc;
+    if ((rc = launch_binning(d, g, keys, keys_alt, desc->sort_impl, desc->sort_segment_hint, st))) return rc;
     mark(kMarkSort, st);
     if (n_instances_host)
-        PS_CUDA_CHECK(cudaMemcpyAsync(n_instances_host, g.n_instances, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        PS_CUDA_CHECK(cudaMemcpyAsync(n_instances_host, g.n_instances, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     if ((rc = launch_composite_forward(d, I, g, keys, final_T, n_contrib, out_color, st))) return rc;
     mark(kMarkCompositeFwd, st);
     if (out_radii)

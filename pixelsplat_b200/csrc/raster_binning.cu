@@ -59,25 +59,57 @@ k_tile_scan(int n, const uint32_t *__restrict__ count, uint32_t *__restrict__ st
     if (tid == 0) *n_instances = (long long)carry_s;
 }
 
+// longest (view, tile) segment -> n_instances[1]; lets the host pick the sort configuration
+__global__ void k_tile_max(int n, const uint32_t *__restrict__ count, long long *__restrict__ out) {
+    uint32_t m = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, count[i]);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(reinterpret_cast<unsigned long long *>(out + 1), (unsigned long long)m);
+}
+
 // ---------------------------------------------------------------- scatter
 constexpr int kScatterThreads = 256;
+constexpr int kScatterMaxSmemTiles = 8192;
 
+// One CTA = 256 consecutive Gaussians of one view.  Slots are reserved per (CTA, tile) with a
+// single global atomic; ranks inside the CTA come from shared-memory atomics.  (Consecutive
+// Gaussians are neighbouring context pixels and land on a handful of tiles, so per-instance
+// global atomics serialise on ~tiles addresses: 68 us -> a few us at configs[1].)
 __global__ void __launch_bounds__(kScatterThreads)
-k_scatter(Dims d, Geom geo, unsigned long long *__restrict__ keys) {
-    if (*geo.n_instances > d.capacity) return;  // truncated call: caller re-runs with more room
-    const size_t vg = (size_t)blockIdx.x * kScatterThreads + threadIdx.x;
-    const size_t total = (size_t)d.S * d.V * d.P;
-    if (vg >= total) return;
-    if (geo.radii[vg] <= 0) return;
-    const int vid = (int)(vg / d.P);
-    const uint32_t g = (uint32_t)(vg - (size_t)vid * d.P);
-    const ushort4 r = geo.rect[vg];
-    const unsigned long long key = ((unsigned long long)__float_as_uint(geo.depth[vg]) << 32) | g;
+k_scatter(Dims d, Geom geo, unsigned long long *__restrict__ keys, int use_smem) {
+    extern __shared__ uint32_t s_scatter[];          // cnt[tiles], base[tiles]
+    if (*geo.n_instances > d.capacity) return;       // truncated call: caller re-runs with more room
+    const int vid = blockIdx.y;
+    const int g = blockIdx.x * kScatterThreads + threadIdx.x;
+    uint32_t *cnt = s_scatter, *base = s_scatter + d.tiles;
     uint32_t *cur = geo.tile_cursor + (size_t)vid * d.tiles;
+    const size_t vg = (size_t)vid * d.P + g;
+    const bool vis = g < d.P && geo.radii[vg] > 0;
+    ushort4 r = make_ushort4(0, 0, 0, 0);
+    unsigned long long key = 0;
+    if (vis) {
+        r = geo.rect[vg];
+        key = ((unsigned long long)__float_as_uint(geo.depth[vg]) << 32) | (uint32_t)g;
+    }
+    if (!use_smem) {
+        for (int ty = r.y; ty < r.w; ++ty)
+            for (int tx = r.x; tx < r.z; ++tx) keys[atomicAdd(&cur[ty * d.gx + tx], 1u)] = key;
+        return;
+    }
+    for (int i = threadIdx.x; i < d.tiles; i += kScatterThreads) cnt[i] = 0;
+    __syncthreads();
+    for (int ty = r.y; ty < r.w; ++ty)
+        for (int tx = r.x; tx < r.z; ++tx) atomicAdd(&cnt[ty * d.gx + tx], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < d.tiles; i += kScatterThreads) {
+        const uint32_t c = cnt[i];
+        if (c) { base[i] = atomicAdd(&cur[i], c); cnt[i] = 0; }
+    }
+    __syncthreads();
     for (int ty = r.y; ty < r.w; ++ty)
         for (int tx = r.x; tx < r.z; ++tx) {
-            const uint32_t slot = atomicAdd(&cur[ty * d.gx + tx], 1u);
-            keys[slot] = key;
+            const int t = ty * d.gx + tx;
+            keys[base[t] + atomicAdd(&cnt[t], 1u)] = key;
         }
 }
 
@@ -96,13 +128,13 @@ __global__ void __launch_bounds__(kSortThreads)
 k_tile_sort(const uint32_t *__restrict__ tile_start, const uint32_t *__restrict__ tile_count,
             const long long *__restrict__ n_instances, long long capacity,
             unsigned long long *__restrict__ keys, unsigned long long *__restrict__ keys_alt,
-            int smem_cap, int min_n, int max_n, int id_bits) {
+            int smem_cap, int id_bits) {
     static_assert(kSortThreads == 256, "one thread per 8-bit digit");
     extern __shared__ __align__(16) unsigned char s_raw[];
     if (*n_instances > capacity) return;
     const int seg = blockIdx.x;
     const int n = (int)tile_count[seg];
-    if (n < 2 || n <= min_n || n > max_n) return;  // trivial, or handled by the other launch
+    if (n < 2) return;
     const uint32_t s0 = tile_start[seg];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -200,16 +232,27 @@ static size_t sort_smem_bytes(int cap) {
     return sizeof(uint32_t) * (kSortWarps * 256 + 256 + 16) + sizeof(unsigned long long) * 2 * (size_t)cap;
 }
 
-constexpr int kSortCapSmall = 2048;    // 32 KB of keys -> several CTAs per SM
-constexpr int kSortCapLarge = 12288;   // 192 KB of keys -> one CTA per SM; beyond: global ping-pong
+// Shared-memory capacities (keys) the host may choose from; a segment longer than the launch's
+// capacity is still sorted correctly, ping-ponging through HBM.
+static const int kSortCaps[] = {1024, 2048, 4096, 8192, 12288};
 
 int launch_binning(const Dims &d, const Geom &g, unsigned long long *keys,
-                   unsigned long long *keys_alt, int sort_impl, cudaStream_t st) {
+                   unsigned long long *keys_alt, int sort_impl, int segment_hint, cudaStream_t st) {
     const int n_seg = d.S * d.V * d.tiles;
     k_tile_scan<<<1, kScanThreads, 0, st>>>(n_seg, g.tile_count, g.tile_start, g.tile_cursor, g.n_instances);
     PS_LAUNCH_CHECK("k_tile_scan");
-    const size_t total = (size_t)d.S * d.V * d.P;
-    k_scatter<<<(unsigned)((total + kScatterThreads - 1) / kScatterThreads), kScatterThreads, 0, st>>>(d, g, keys);
+    PS_CUDA_CHECK(cudaMemsetAsync(g.n_instances + 1, 0, sizeof(long long), st));
+    k_tile_max<<<min(148, (n_seg + 255) / 256), 256, 0, st>>>(n_seg, g.tile_count, g.n_instances);
+    PS_LAUNCH_CHECK("k_tile_max");
+    const int use_smem = d.tiles <= kScatterMaxSmemTiles;
+    static bool scatter_attr = false;
+    if (!scatter_attr) {
+        PS_CUDA_CHECK(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(2 * sizeof(uint32_t) * kScatterMaxSmemTiles)));
+        scatter_attr = true;
+    }
+    dim3 sgrid((d.P + kScatterThreads - 1) / kScatterThreads, d.S * d.V);
+    k_scatter<<<sgrid, kScatterThreads, use_smem ? 2 * sizeof(uint32_t) * d.tiles : 0, st>>>(d, g, keys, use_smem);
     PS_LAUNCH_CHECK("k_scatter");
     mark(kMarkScatter, st);
 
@@ -221,8 +264,6 @@ int launch_binning(const Dims &d, const Geom &g, unsigned long long *keys,
         // the native sort in tests; needs n_instances <= capacity, guaranteed by the caller).
         size_t temp = 0;
         cub::DoubleBuffer<unsigned long long> db(keys, keys_alt);
-        // tile_start has n_seg entries; end offsets = start + count: build them in tile_cursor,
-        // which after k_scatter already equals start + count.
         PS_CUDA_CHECK(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, temp, db, (int)d.capacity, n_seg,
                                                               g.tile_start, g.tile_cursor, 0, 64, st));
         void *tmp = nullptr;
@@ -239,16 +280,17 @@ int launch_binning(const Dims &d, const Geom &g, unsigned long long *keys,
     static bool attr_set = false;
     if (!attr_set) {
         PS_CUDA_CHECK(cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sort_smem_bytes(kSortCapLarge)));
+                                           (int)sort_smem_bytes(12288)));
         attr_set = true;
     }
-    k_tile_sort<<<n_seg, kSortThreads, sort_smem_bytes(kSortCapSmall), st>>>(
-        g.tile_start, g.tile_count, g.n_instances, d.capacity, keys, keys_alt, kSortCapSmall, 0, kSortCapSmall, id_bits);
-    PS_LAUNCH_CHECK("k_tile_sort(small)");
-    // second launch only does work for segments longer than kSortCapSmall
-    k_tile_sort<<<n_seg, kSortThreads, sort_smem_bytes(kSortCapLarge), st>>>(
-        g.tile_start, g.tile_count, g.n_instances, d.capacity, keys, keys_alt, kSortCapLarge, kSortCapSmall, 0x7fffffff, id_bits);
-    PS_LAUNCH_CHECK("k_tile_sort(large)");
+    int cap = 2048;   // no hint: typical 256x256 tiles fit; longer ones take the HBM ping-pong
+    if (segment_hint > 0) {
+        cap = kSortCaps[4];
+        for (int i = 4; i >= 0; --i) if (segment_hint <= kSortCaps[i]) cap = kSortCaps[i];
+    }
+    k_tile_sort<<<n_seg, kSortThreads, sort_smem_bytes(cap), st>>>(
+        g.tile_start, g.tile_count, g.n_instances, d.capacity, keys, keys_alt, cap, id_bits);
+    PS_LAUNCH_CHECK("k_tile_sort");
     return PS_OK;
 }
 

@@ -132,6 +132,74 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Sum each of 16 per-lane values over the warp with 16 shuffles instead of 80: at every step a
+// lane keeps half of its values and hands the other half to its partner.  On return lane 2i
+// (and 2i+1) holds the warp total of v[i].
+__device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int half = 8, dist = 16; half >= 1; half >>= 1, dist >>= 1) {
+        const bool up = (lane & dist) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float keep = up ? v[i + half] : v[i];
+            const float send = up ? v[i] : v[i + half];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, dist);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// Per-pixel backward of one list entry.  Returns whether the entry contributed;
+// g[0..7] = d_mean2d.xy, d_conic.xyz, d_color.rgb ; op = d_opacity.
+struct PixelState {
+    float T, acc_r, acc_g, acc_b, last_alpha, lc_r, lc_g, lc_b;
+};
+
+__device__ __forceinline__ bool pixel_bwd(bool in_range, const float2 exy, const float4 eco, const float4 ergb,
+                                          float px, float py, float dpr, float dpg, float dpb, float T_final,
+                                          float bg_dot, float ddelx_dx, float ddely_dy, PixelState &st,
+                                          float *g, float &op) {
+    bool active = in_range;
+    float dx = 0.0f, dy = 0.0f, G = 0.0f, alpha = 0.0f;
+    if (active) {
+        dx = exy.x - px; dy = exy.y - py;
+        const float power = -0.5f * (eco.x * dx * dx + eco.z * dy * dy) - eco.y * dx * dy;
+        active = !(power > 0.0f);
+        if (active) {
+            G = __expf(power);
+            alpha = fminf(0.99f, eco.w * G);
+            active = !(alpha < kAlphaMin);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] = 0.0f;
+    op = 0.0f;
+    if (active) {
+        st.T = st.T / (1.0f - alpha);
+        const float dchannel_dcolor = alpha * st.T;
+        st.acc_r = st.last_alpha * st.lc_r + (1.0f - st.last_alpha) * st.acc_r;
+        st.acc_g = st.last_alpha * st.lc_g + (1.0f - st.last_alpha) * st.acc_g;
+        st.acc_b = st.last_alpha * st.lc_b + (1.0f - st.last_alpha) * st.acc_b;
+        st.lc_r = ergb.x; st.lc_g = ergb.y; st.lc_b = ergb.z;
+        float dL_dalpha = (ergb.x - st.acc_r) * dpr + (ergb.y - st.acc_g) * dpg + (ergb.z - st.acc_b) * dpb;
+        g[5] = dchannel_dcolor * dpr; g[6] = dchannel_dcolor * dpg; g[7] = dchannel_dcolor * dpb;
+        dL_dalpha *= st.T;
+        st.last_alpha = alpha;
+        dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot;
+        const float dL_dG = eco.w * dL_dalpha;
+        const float gdx = G * dx, gdy = G * dy;
+        const float dG_ddelx = -gdx * eco.x - gdy * eco.y;
+        const float dG_ddely = -gdy * eco.z - gdx * eco.y;
+        g[0] = dL_dG * dG_ddelx * ddelx_dx;
+        g[1] = dL_dG * dG_ddely * ddely_dy;
+        g[2] = -0.5f * gdx * dx * dL_dG;
+        g[3] = -0.5f * gdx * dy * dL_dG;
+        g[4] = -0.5f * gdy * dy * dL_dG;
+        op = G * dL_dalpha;
+    }
+    return active;
+}
+
 __global__ void __launch_bounds__(kCompThreads)
 k_composite_bwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                 const unsigned long long *__restrict__ keys, const float *__restrict__ final_T,
@@ -139,7 +207,7 @@ k_composite_bwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                 ViewGrads vg) {
     __shared__ StageBuf s;
     __shared__ uint32_t s_g[kStage];
-    __shared__ float s_acc[kStage][9];  // mean2d.xy, conic.xyz, opacity, color.rgb
+    __shared__ float s_acc[kStage][9];  // mean2d.xy, conic.xyz, color.rgb, opacity
     __shared__ uint32_t s_max_last;
     const int vid = blockIdx.y, tile = blockIdx.x;
     const int tx = tile % d.gx, ty = tile / d.gx;
@@ -174,11 +242,11 @@ k_composite_bwd(Dims d, Geom geo, const float *__restrict__ bg_all,
     __syncthreads();
     const uint32_t block_last = s_max_last;   // entries at list position >= block_last are unused
 
-    float T = T_final;
-    float acc_r = 0.0f, acc_g = 0.0f, acc_b = 0.0f, last_alpha = 0.0f, lc_r = 0.0f, lc_g = 0.0f, lc_b = 0.0f;
+    PixelState st;
+    st.T = T_final;
+    st.acc_r = st.acc_g = st.acc_b = st.last_alpha = st.lc_r = st.lc_g = st.lc_b = 0.0f;
 
-    // walk positions block_last-1 .. 0, staged in chunks of kStage (chunk k covers the
-    // positions [hi_k - n_k, hi_k) with hi_0 = block_last, highest position first)
+    // walk positions block_last-1 .. 0, staged in chunks of kStage (highest position first)
     for (uint32_t hi = block_last; hi > 0;) {
         const uint32_t n_here = min((uint32_t)kStage, hi);
         // staged index j <-> list position  pos = hi - 1 - j
@@ -198,61 +266,35 @@ k_composite_bwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                 hit = (c.x + e.x >= rx0) && (c.x - e.x <= rx1) && (c.y + e.y >= ry0) && (c.y - e.y <= ry1);
             }
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            // two list entries per iteration: their exp / gradient math is independent (only the
+            // cheap T / colour-behind recurrences chain), and one 16-wide transposed shuffle
+            // reduction serves both
             while (mask) {
-                const int bpos = __ffs(mask) - 1;
+                const int b0 = __ffs(mask) - 1;
                 mask &= mask - 1;
-                const uint32_t jj = jb + (uint32_t)bpos;
-                const uint32_t pos = hi - 1u - jj;
-                struct { float2 xy; float4 co; float4 rgb; } e;
-                e.xy = s.xy[jj]; e.co = s.co[jj]; e.rgb = s.rgb[jj];
-                float g_mx = 0.0f, g_my = 0.0f, g_ca = 0.0f, g_cb = 0.0f, g_cc = 0.0f, g_op = 0.0f;
-                float g_r = 0.0f, g_g = 0.0f, g_b = 0.0f;
-                bool active = pos < last;
-                float dx = 0.0f, dy = 0.0f, G = 0.0f, alpha = 0.0f;
-                if (active) {
-                    dx = e.xy.x - px; dy = e.xy.y - py;
-                    const float power = -0.5f * (e.co.x * dx * dx + e.co.z * dy * dy) - e.co.y * dx * dy;
-                    active = !(power > 0.0f);
-                    if (active) {
-                        G = __expf(power);
-                        alpha = fminf(0.99f, e.co.w * G);
-                        active = !(alpha < kAlphaMin);
-                    }
-                }
-                if (active) {
-                    T = T / (1.0f - alpha);
-                    const float dchannel_dcolor = alpha * T;
-                    acc_r = last_alpha * lc_r + (1.0f - last_alpha) * acc_r;
-                    acc_g = last_alpha * lc_g + (1.0f - last_alpha) * acc_g;
-                    acc_b = last_alpha * lc_b + (1.0f - last_alpha) * acc_b;
-                    lc_r = e.rgb.x; lc_g = e.rgb.y; lc_b = e.rgb.z;
-                    float dL_dalpha = (e.rgb.x - acc_r) * dpr + (e.rgb.y - acc_g) * dpg + (e.rgb.z - acc_b) * dpb;
-                    g_r = dchannel_dcolor * dpr; g_g = dchannel_dcolor * dpg; g_b = dchannel_dcolor * dpb;
-                    dL_dalpha *= T;
-                    last_alpha = alpha;
-                    dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot;
-                    const float dL_dG = e.co.w * dL_dalpha;
-                    const float gdx = G * dx, gdy = G * dy;
-                    const float dG_ddelx = -gdx * e.co.x - gdy * e.co.y;
-                    const float dG_ddely = -gdy * e.co.z - gdx * e.co.y;
-                    g_mx = dL_dG * dG_ddelx * ddelx_dx;
-                    g_my = dL_dG * dG_ddely * ddely_dy;
-                    g_ca = -0.5f * gdx * dx * dL_dG;
-                    g_cb = -0.5f * gdx * dy * dL_dG;
-                    g_cc = -0.5f * gdy * dy * dL_dG;
-                    g_op = G * dL_dalpha;
-                }
-                if (!__any_sync(0xffffffffu, active)) continue;
-                g_mx = warp_sum(g_mx); g_my = warp_sum(g_my);
-                g_ca = warp_sum(g_ca); g_cb = warp_sum(g_cb); g_cc = warp_sum(g_cc);
-                g_op = warp_sum(g_op);
-                g_r = warp_sum(g_r); g_g = warp_sum(g_g); g_b = warp_sum(g_b);
-                if (lane == 0) {
-                    float *a = s_acc[jj];
-                    atomicAdd(a + 0, g_mx); atomicAdd(a + 1, g_my);
-                    atomicAdd(a + 2, g_ca); atomicAdd(a + 3, g_cb); atomicAdd(a + 4, g_cc);
-                    atomicAdd(a + 5, g_op);
-                    atomicAdd(a + 6, g_r); atomicAdd(a + 7, g_g); atomicAdd(a + 8, g_b);
+                const bool two = mask != 0;
+                const int b1 = two ? __ffs(mask) - 1 : b0;
+                mask &= mask - 1;   // no-op when already 0
+                const uint32_t j0 = jb + (uint32_t)b0, j1 = jb + (uint32_t)b1;
+                float v[16], op0, op1;
+                const bool a0 = pixel_bwd((hi - 1u - j0) < last, s.xy[j0], s.co[j0], s.rgb[j0], px, py, dpr, dpg, dpb,
+                                          T_final, bg_dot, ddelx_dx, ddely_dy, st, v, op0);
+                const bool a1 = pixel_bwd(two && (hi - 1u - j1) < last, s.xy[j1], s.co[j1], s.rgb[j1], px, py, dpr,
+                                          dpg, dpb, T_final, bg_dot, ddelx_dx, ddely_dy, st, v + 8, op1);
+                const unsigned any0 = __ballot_sync(0xffffffffu, a0), any1 = __ballot_sync(0xffffffffu, a1);
+                if ((any0 | any1) == 0u) continue;
+                const float tot = transpose_reduce16(v, lane);
+                op0 = warp_sum(op0);
+                op1 = warp_sum(op1);
+                if ((lane & 1) == 0) {
+                    const int vi = lane >> 1;               // 0..15
+                    const bool second = vi >= 8;
+                    if (second ? (any1 != 0u) : (any0 != 0u))
+                        atomicAdd(&s_acc[second ? j1 : j0][vi & 7], tot);
+                } else if (lane == 1) {
+                    if (any0) atomicAdd(&s_acc[j0][8], op0);
+                } else if (lane == 3) {
+                    if (any1) atomicAdd(&s_acc[j1][8], op1);
                 }
             }
         }
@@ -268,8 +310,8 @@ k_composite_bwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                 float *c = reinterpret_cast<float *>(vg.d_conic + o);
                 float *col = reinterpret_cast<float *>(vg.d_color + o);
                 atomicAdd(m + 0, a[0]); atomicAdd(m + 1, a[1]);
-                atomicAdd(c + 0, a[2]); atomicAdd(c + 1, a[3]); atomicAdd(c + 2, a[4]); atomicAdd(c + 3, a[5]);
-                atomicAdd(col + 0, a[6]); atomicAdd(col + 1, a[7]); atomicAdd(col + 2, a[8]);
+                atomicAdd(c + 0, a[2]); atomicAdd(c + 1, a[3]); atomicAdd(c + 2, a[4]); atomicAdd(c + 3, a[8]);
+                atomicAdd(col + 0, a[5]); atomicAdd(col + 1, a[6]); atomicAdd(col + 2, a[7]);
             }
         }
         __syncthreads();

@@ -69,85 +69,58 @@ __device__ __forceinline__ void compute_cov2d(float px, float py, float pz, cons
     o.c = o.m1[0] * v1x + o.m1[1] * v1y + o.m1[2] * v1z + 0.3f;
 }
 
-// Real SH basis for a unit direction; entries >= (deg+1)^2 are left untouched.
-__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float b[25]) {
-    b[0] = kShC0;
+// Real SH up to degree 4 (3DGS sign convention), visited term by term: f(k, Y_k, dY_k/dx,
+// dY_k/dy, dY_k/dz) is called for k = 0 .. (deg+1)^2-1 in order, with x, y, z treated as
+// independent variables in the derivatives.  Consuming the terms as they are produced keeps
+// the 25 (or 100, with derivatives) values out of registers; callers that ignore the
+// derivatives pay nothing for them.  The value expressions are written exactly as in the oracle
+// (operand order matters: the forward kernel is compiled without FMA contraction).
+template <class F>
+__device__ __forceinline__ void sh_for_each(int deg, float x, float y, float z, F &&f) {
+    f(0, kShC0, 0.0f, 0.0f, 0.0f);
     if (deg < 1) return;
-    b[1] = -kShC1 * y;
-    b[2] = kShC1 * z;
-    b[3] = -kShC1 * x;
-    if (deg < 2) return;
-    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-    b[4] = 1.0925484305920792f * xy;
-    b[5] = -1.0925484305920792f * yz;
-    b[6] = 0.31539156525252005f * (2.0f * zz - xx - yy);
-    b[7] = -1.0925484305920792f * xz;
-    b[8] = 0.5462742152960396f * (xx - yy);
-    if (deg < 3) return;
-    b[9] = -0.5900435899266435f * y * (3.0f * xx - yy);
-    b[10] = 2.890611442640554f * xy * z;
-    b[11] = -0.4570457994644658f * y * (4.0f * zz - xx - yy);
-    b[12] = 0.3731763325901154f * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
-    b[13] = -0.4570457994644658f * x * (4.0f * zz - xx - yy);
-    b[14] = 1.445305721320277f * z * (xx - yy);
-    b[15] = -0.5900435899266435f * x * (xx - 3.0f * yy);
-    if (deg < 4) return;
-    b[16] = 2.5033429417967046f * xy * (xx - yy);
-    b[17] = -1.7701307697799304f * yz * (3.0f * xx - yy);
-    b[18] = 0.9461746957575601f * xy * (7.0f * zz - 1.0f);
-    b[19] = -0.6690465435572892f * yz * (7.0f * zz - 3.0f);
-    b[20] = 0.10578554691520431f * (zz * (35.0f * zz - 30.0f) + 3.0f);
-    b[21] = -0.6690465435572892f * xz * (7.0f * zz - 3.0f);
-    b[22] = 0.47308734787878004f * (xx - yy) * (7.0f * zz - 1.0f);
-    b[23] = -1.7701307697799304f * xz * (xx - 3.0f * yy);
-    b[24] = 0.6258357354491761f * (xx * (xx - 3.0f * yy) - yy * (3.0f * xx - yy));
-}
-
-// d basis / d(x, y, z) with x, y, z treated as independent variables.
-__device__ __forceinline__ void sh_basis_grad(int deg, float x, float y, float z, float dx[25],
-                                              float dy[25], float dz[25]) {
-#pragma unroll
-    for (int i = 0; i < 25; ++i) dx[i] = dy[i] = dz[i] = 0.0f;
-    if (deg < 1) return;
-    dy[1] = -kShC1;
-    dz[2] = kShC1;
-    dx[3] = -kShC1;
+    f(1, -kShC1 * y, 0.0f, -kShC1, 0.0f);
+    f(2, kShC1 * z, 0.0f, 0.0f, kShC1);
+    f(3, -kShC1 * x, -kShC1, 0.0f, 0.0f);
     if (deg < 2) return;
     const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
     {
         const float c0 = 1.0925484305920792f, c2 = 0.31539156525252005f, c4 = 0.5462742152960396f;
-        dx[4] = c0 * y;          dy[4] = c0 * x;
-        dy[5] = -c0 * z;         dz[5] = -c0 * y;
-        dx[6] = -2.0f * c2 * x;  dy[6] = -2.0f * c2 * y;  dz[6] = 4.0f * c2 * z;
-        dx[7] = -c0 * z;         dz[7] = -c0 * x;
-        dx[8] = 2.0f * c4 * x;   dy[8] = -2.0f * c4 * y;
+        f(4, 1.0925484305920792f * xy, c0 * y, c0 * x, 0.0f);
+        f(5, -1.0925484305920792f * yz, 0.0f, -c0 * z, -c0 * y);
+        f(6, 0.31539156525252005f * (2.0f * zz - xx - yy), -2.0f * c2 * x, -2.0f * c2 * y, 4.0f * c2 * z);
+        f(7, -1.0925484305920792f * xz, -c0 * z, 0.0f, -c0 * x);
+        f(8, 0.5462742152960396f * (xx - yy), 2.0f * c4 * x, -2.0f * c4 * y, 0.0f);
     }
     if (deg < 3) return;
     {
         const float c0 = -0.5900435899266435f, c1 = 2.890611442640554f, c2 = -0.4570457994644658f,
                     c3 = 0.3731763325901154f, c5 = 1.445305721320277f;
-        dx[9] = c0 * 6.0f * xy;                       dy[9] = c0 * (3.0f * xx - 3.0f * yy);
-        dx[10] = c1 * yz;  dy[10] = c1 * xz;          dz[10] = c1 * xy;
-        dx[11] = c2 * -2.0f * xy;  dy[11] = c2 * (4.0f * zz - xx - 3.0f * yy);  dz[11] = c2 * 8.0f * yz;
-        dx[12] = c3 * -6.0f * xz;  dy[12] = c3 * -6.0f * yz;  dz[12] = c3 * (6.0f * zz - 3.0f * xx - 3.0f * yy);
-        dx[13] = c2 * (4.0f * zz - 3.0f * xx - yy);  dy[13] = c2 * -2.0f * xy;  dz[13] = c2 * 8.0f * xz;
-        dx[14] = c5 * 2.0f * xz;   dy[14] = c5 * -2.0f * yz;  dz[14] = c5 * (xx - yy);
-        dx[15] = c0 * (3.0f * xx - 3.0f * yy);       dy[15] = c0 * -6.0f * xy;
+        f(9, -0.5900435899266435f * y * (3.0f * xx - yy), c0 * 6.0f * xy, c0 * (3.0f * xx - 3.0f * yy), 0.0f);
+        f(10, 2.890611442640554f * xy * z, c1 * yz, c1 * xz, c1 * xy);
+        f(11, -0.4570457994644658f * y * (4.0f * zz - xx - yy), c2 * -2.0f * xy, c2 * (4.0f * zz - xx - 3.0f * yy), c2 * 8.0f * yz);
+        f(12, 0.3731763325901154f * z * (2.0f * zz - 3.0f * xx - 3.0f * yy), c3 * -6.0f * xz, c3 * -6.0f * yz,
+          c3 * (6.0f * zz - 3.0f * xx - 3.0f * yy));
+        f(13, -0.4570457994644658f * x * (4.0f * zz - xx - yy), c2 * (4.0f * zz - 3.0f * xx - yy), c2 * -2.0f * xy, c2 * 8.0f * xz);
+        f(14, 1.445305721320277f * z * (xx - yy), c5 * 2.0f * xz, c5 * -2.0f * yz, c5 * (xx - yy));
+        f(15, -0.5900435899266435f * x * (xx - 3.0f * yy), c0 * (3.0f * xx - 3.0f * yy), c0 * -6.0f * xy, 0.0f);
     }
     if (deg < 4) return;
     {
         const float c0 = 2.5033429417967046f, c1 = -1.7701307697799304f, c2 = 0.9461746957575601f,
                     c3 = -0.6690465435572892f, c4 = 0.10578554691520431f, c6 = 0.47308734787878004f,
                     c8 = 0.6258357354491761f;
-        dx[16] = c0 * (3.0f * xx * y - yy * y);       dy[16] = c0 * (xx * x - 3.0f * x * yy);
-        dx[17] = c1 * 6.0f * xy * z;  dy[17] = c1 * z * (3.0f * xx - 3.0f * yy);  dz[17] = c1 * y * (3.0f * xx - yy);
-        dx[18] = c2 * y * (7.0f * zz - 1.0f);  dy[18] = c2 * x * (7.0f * zz - 1.0f);  dz[18] = c2 * 14.0f * xy * z;
-        dy[19] = c3 * z * (7.0f * zz - 3.0f);  dz[19] = c3 * y * (21.0f * zz - 3.0f);
-        dz[20] = c4 * (140.0f * zz * z - 60.0f * z);
-        dx[21] = c3 * z * (7.0f * zz - 3.0f);  dz[21] = c3 * x * (21.0f * zz - 3.0f);
-        dx[22] = c6 * 2.0f * x * (7.0f * zz - 1.0f);  dy[22] = c6 * -2.0f * y * (7.0f * zz - 1.0f);  dz[22] = c6 * 14.0f * z * (xx - yy);
-        dx[23] = c1 * z * (3.0f * xx - 3.0f * yy);  dy[23] = c1 * -6.0f * xy * z;  dz[23] = c1 * x * (xx - 3.0f * yy);
-        dx[24] = c8 * (4.0f * xx * x - 12.0f * x * yy);  dy[24] = c8 * (4.0f * yy * y - 12.0f * xx * y);
+        f(16, 2.5033429417967046f * xy * (xx - yy), c0 * (3.0f * xx * y - yy * y), c0 * (xx * x - 3.0f * x * yy), 0.0f);
+        f(17, -1.7701307697799304f * yz * (3.0f * xx - yy), c1 * 6.0f * xy * z, c1 * z * (3.0f * xx - 3.0f * yy), c1 * y * (3.0f * xx - yy));
+        f(18, 0.9461746957575601f * xy * (7.0f * zz - 1.0f), c2 * y * (7.0f * zz - 1.0f), c2 * x * (7.0f * zz - 1.0f), c2 * 14.0f * xy * z);
+        f(19, -0.6690465435572892f * yz * (7.0f * zz - 3.0f), 0.0f, c3 * z * (7.0f * zz - 3.0f), c3 * y * (21.0f * zz - 3.0f));
+        f(20, 0.10578554691520431f * (zz * (35.0f * zz - 30.0f) + 3.0f), 0.0f, 0.0f, c4 * (140.0f * zz * z - 60.0f * z));
+        f(21, -0.6690465435572892f * xz * (7.0f * zz - 3.0f), c3 * z * (7.0f * zz - 3.0f), 0.0f, c3 * x * (21.0f * zz - 3.0f));
+        f(22, 0.47308734787878004f * (xx - yy) * (7.0f * zz - 1.0f), c6 * 2.0f * x * (7.0f * zz - 1.0f), c6 * -2.0f * y * (7.0f * zz - 1.0f),
+          c6 * 14.0f * z * (xx - yy));
+        f(23, -1.7701307697799304f * xz * (xx - 3.0f * yy), c1 * z * (3.0f * xx - 3.0f * yy), c1 * -6.0f * xy * z, c1 * x * (xx - 3.0f * yy));
+        f(24, 0.6258357354491761f * (xx * (xx - 3.0f * yy) - yy * (3.0f * xx - yy)), c8 * (4.0f * xx * x - 12.0f * x * yy),
+          c8 * (4.0f * yy * y - 12.0f * xx * y), 0.0f);
     }
 }
 

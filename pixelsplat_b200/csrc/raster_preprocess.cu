@@ -13,7 +13,7 @@ namespace ps {
 
 constexpr int kPreThreads = 128;
 
-__global__ void __launch_bounds__(kPreThreads)
+__global__ void __launch_bounds__(kPreThreads, 4)
 k_preprocess(Dims d, Inputs in, Geom geo, int use_smem_hist) {
     extern __shared__ uint32_t s_hist[];  // [V * tiles] when use_smem_hist
     const int scene = blockIdx.y;
@@ -77,18 +77,20 @@ k_preprocess(Dims d, Inputs in, Geom geo, int use_smem_hist) {
                 const float ddx = px - cx, ddy = py - cy, ddz = pz - cz;
                 const float len = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
                 const float x = ddx / len, y = ddy / len, z = ddz / len;
-                float basis[25];
-                sh_basis(d.deg, x, y, z, basis);
-                const int nb = (d.deg + 1) * (d.deg + 1);
+                float acc[3] = {0.0f, 0.0f, 0.0f};
+                const int M = d.M, layout = d.sh_layout;
+                sh_for_each(d.deg, x, y, z, [&](int k, float Y, float, float, float) {
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const float c = __ldg(sh + sh_index(layout, M, k, ch));
+                        acc[ch] = k == 0 ? Y * c : acc[ch] + Y * c;
+                    }
+                });
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
-                    float acc = basis[0] * __ldg(sh + sh_index(d.sh_layout, d.M, 0, ch));
-#pragma unroll
-                    for (int k = 1; k < 25; ++k)
-                        if (k < nb) acc = acc + basis[k] * __ldg(sh + sh_index(d.sh_layout, d.M, k, ch));
-                    acc = acc + 0.5f;
-                    if (acc < 0.0f) clamp_bits |= (uint8_t)(1u << ch);
-                    rgb[ch] = fmaxf(acc, 0.0f);
+                    const float a = acc[ch] + 0.5f;
+                    if (a < 0.0f) clamp_bits |= (uint8_t)(1u << ch);
+                    rgb[ch] = fmaxf(a, 0.0f);
                 }
             } else {
                 const float *__restrict__ col = in.sh + sg * 3;

@@ -13,21 +13,32 @@
 namespace ps {
 
 constexpr int kPreBwdThreads = 128;
+constexpr int kPreBwdWarps = kPreBwdThreads / 32;
 
-__global__ void __launch_bounds__(kPreBwdThreads)
-k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out) {
+// dL/dSH is staged per warp in shared memory ([32 Gaussians][3M floats], row stride padded to an
+// odd word count so the per-lane rows are bank-conflict free) and written out as one contiguous
+// 32*3M-float run with 16-byte stores.  A thread-per-Gaussian direct write would issue 3M
+// 4-byte stores at a 12M-byte stride: 8x the L2 write transactions, which was the limiter
+// (202 us -> see profiles/).
+__global__ void __launch_bounds__(kPreBwdThreads, 4)
+k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out, int row_stride) {
+    extern __shared__ float s_dsh[];   // [warps][32][row_stride]
     const int scene = blockIdx.y;
-    const int g = blockIdx.x * kPreBwdThreads + threadIdx.x;
-    if (g >= d.P) return;
-    const size_t sg = (size_t)scene * d.P + g;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g0 = blockIdx.x * kPreBwdThreads + warp * 32;   // first Gaussian of this warp
+    const int g = g0 + lane;
+    const bool live = g < d.P;
+    const size_t sg = (size_t)scene * d.P + (live ? g : 0);
     const bool truncated = *geo.n_instances > d.capacity;
-    const float mx0 = in.means[3 * sg + 0], my0 = in.means[3 * sg + 1], mz0 = in.means[3 * sg + 2];
     const int cov_n = d.cov_layout == PS_COV_TRIU6 ? 6 : 9;
-    const float *covp = in.cov + sg * cov_n;
     const int sh_n = d.M > 0 ? 3 * d.M : 3;
+    float *row = s_dsh + ((size_t)warp * 32 + lane) * row_stride;
+    const int M = d.M, layout = d.sh_layout;
+
+    float mx0 = 0.0f, my0 = 0.0f, mz0 = 0.0f;
+    if (live) { mx0 = in.means[3 * sg + 0]; my0 = in.means[3 * sg + 1]; mz0 = in.means[3 * sg + 2]; }
+    const float *covp = in.cov + sg * cov_n;
     const float *__restrict__ sh = in.sh + sg * (size_t)sh_n;
-    float *__restrict__ dsh = out.d_sh + sg * (size_t)sh_n;
-    const int nb = (d.deg + 1) * (d.deg + 1);
 
     float dmx = 0.0f, dmy = 0.0f, dmz = 0.0f, dop = 0.0f;
     float dcov[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
@@ -36,9 +47,9 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
 
     for (int v = 0; v < d.V; ++v) {
         const int vid = scene * d.V + v;
-        const size_t vg = (size_t)vid * d.P + g;
-        const bool vis = !truncated && geo.radii[vg] > 0;
-        if (out.d_means2d) {
+        const size_t vg = (size_t)vid * d.P + (live ? g : 0);
+        const bool vis = live && !truncated && geo.radii[vg] > 0;
+        if (live && out.d_means2d) {
             float *m2 = out.d_means2d + 3 * vg;
             const float2 t = vis ? vgr.d_mean2d[vg] : make_float2(0.0f, 0.0f);
             m2[0] = t.x; m2[1] = t.y; m2[2] = 0.0f;
@@ -65,22 +76,18 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
         const float denom2inv = 1.0f / (denom * denom + 0.0000001f);
         float dL_da = 0.0f, dL_db = 0.0f, dL_dc = 0.0f;
         const float *m0 = cv.m0, *m1 = cv.m1;
-        float vd[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
         if (denom2inv != 0.0f) {
             dL_da = denom2inv * (-c * c * gc.x + 2.0f * b * c * gc.y + (denom - a * c) * gc.z);
             dL_dc = denom2inv * (-a * a * gc.z + 2.0f * a * b * gc.y + (denom - a * c) * gc.x);
             dL_db = denom2inv * 2.0f * (b * c * gc.x - (denom + 2.0f * b * b) * gc.y + a * b * gc.z);
-            vd[0] = m0[0] * m0[0] * dL_da + m0[0] * m1[0] * dL_db + m1[0] * m1[0] * dL_dc;
-            vd[3] = m0[1] * m0[1] * dL_da + m0[1] * m1[1] * dL_db + m1[1] * m1[1] * dL_dc;
-            vd[5] = m0[2] * m0[2] * dL_da + m0[2] * m1[2] * dL_db + m1[2] * m1[2] * dL_dc;
-            vd[1] = 2.0f * m0[0] * m0[1] * dL_da + (m0[0] * m1[1] + m0[1] * m1[0]) * dL_db + 2.0f * m1[0] * m1[1] * dL_dc;
-            vd[2] = 2.0f * m0[0] * m0[2] * dL_da + (m0[0] * m1[2] + m0[2] * m1[0]) * dL_db + 2.0f * m1[0] * m1[2] * dL_dc;
-            vd[4] = 2.0f * m0[2] * m0[1] * dL_da + (m0[1] * m1[2] + m0[2] * m1[1]) * dL_db + 2.0f * m1[1] * m1[2] * dL_dc;
+            const float s2 = sc * sc;
+            dcov[0] += s2 * (m0[0] * m0[0] * dL_da + m0[0] * m1[0] * dL_db + m1[0] * m1[0] * dL_dc);
+            dcov[3] += s2 * (m0[1] * m0[1] * dL_da + m0[1] * m1[1] * dL_db + m1[1] * m1[1] * dL_dc);
+            dcov[5] += s2 * (m0[2] * m0[2] * dL_da + m0[2] * m1[2] * dL_db + m1[2] * m1[2] * dL_dc);
+            dcov[1] += s2 * (2.0f * m0[0] * m0[1] * dL_da + (m0[0] * m1[1] + m0[1] * m1[0]) * dL_db + 2.0f * m1[0] * m1[1] * dL_dc);
+            dcov[2] += s2 * (2.0f * m0[0] * m0[2] * dL_da + (m0[0] * m1[2] + m0[2] * m1[0]) * dL_db + 2.0f * m1[0] * m1[2] * dL_dc);
+            dcov[4] += s2 * (2.0f * m0[2] * m0[1] * dL_da + (m0[1] * m1[2] + m0[2] * m1[1]) * dL_db + 2.0f * m1[1] * m1[2] * dL_dc);
         }
-        const float s2 = sc * sc;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) dcov[i] += vd[i] * s2;
-
         // dL/dM (rows) from a = m0 S m0, b = m0 S m1, c = m1 S m1
         const float S[3][3] = {{s6[0], s6[1], s6[2]}, {s6[1], s6[3], s6[4]}, {s6[2], s6[4], s6[5]}};
         float dM0[3], dM1[3];
@@ -114,35 +121,31 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
         gy += (pm[4] * m_w - pm[7] * mul1) * g2.x + (pm[5] * m_w - pm[7] * mul2) * g2.y;
         gz += (pm[8] * m_w - pm[11] * mul1) * g2.x + (pm[9] * m_w - pm[11] * mul2) * g2.y;
 
-        if (d.M > 0) {
+        if (M > 0) {
             const float cx = in.campos[3 * vid], cy = in.campos[3 * vid + 1], cz = in.campos[3 * vid + 2];
             const float ddx = px - cx, ddy = py - cy, ddz = pz - cz;
             const float len2 = ddx * ddx + ddy * ddy + ddz * ddz;
             const float len = sqrtf(len2);
             const float x = ddx / len, y = ddy / len, z = ddz / len;
-            float basis[25], bx[25], by[25], bz[25];
-            sh_basis(d.deg, x, y, z, basis);
-            sh_basis_grad(d.deg, x, y, z, bx, by, bz);
             const uint8_t cl = geo.clamped[vg];
             const float dl[3] = {(cl & 1) ? 0.0f : gcol.x, (cl & 2) ? 0.0f : gcol.y, (cl & 4) ? 0.0f : gcol.z};
             float dLdx = 0.0f, dLdy = 0.0f, dLdz = 0.0f;
+            const bool first = !sh_written;
+            sh_for_each(d.deg, x, y, z, [&](int k, float Y, float Yx, float Yy, float Yz) {
 #pragma unroll
-            for (int k = 0; k < 25; ++k) {
-                if (k < nb) {
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        const int idx = sh_index(d.sh_layout, d.M, k, ch);
-                        const float coef = __ldg(sh + idx);
-                        const float val = basis[k] * dl[ch];
-                        if (sh_written) dsh[idx] += val; else dsh[idx] = val;
-                        const float cd = coef * dl[ch];
-                        dLdx += bx[k] * cd; dLdy += by[k] * cd; dLdz += bz[k] * cd;
-                    }
+                for (int ch = 0; ch < 3; ++ch) {
+                    const int idx = sh_index(layout, M, k, ch);
+                    const float val = Y * dl[ch];
+                    row[idx] = first ? val : row[idx] + val;
+                    const float cd = __ldg(sh + idx) * dl[ch];
+                    dLdx += Yx * cd; dLdy += Yy * cd; dLdz += Yz * cd;
                 }
+            });
+            if (first) {
+                const int nb = (d.deg + 1) * (d.deg + 1);
+                for (int k = nb; k < M; ++k)
+                    for (int ch = 0; ch < 3; ++ch) row[sh_index(layout, M, k, ch)] = 0.0f;
             }
-            if (!sh_written)
-                for (int k = nb; k < d.M; ++k)
-                    for (int ch = 0; ch < 3; ++ch) dsh[sh_index(d.sh_layout, d.M, k, ch)] = 0.0f;
             sh_written = true;
             const float inv3 = 1.0f / (len2 * len);
             gx += ((len2 - ddx * ddx) * dLdx - ddy * ddx * dLdy - ddz * ddx * dLdz) * inv3;
@@ -154,29 +157,62 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
         dmx += gx * sc; dmy += gy * sc; dmz += gz * sc;
     }
 
-    out.d_means[3 * sg + 0] = dmx; out.d_means[3 * sg + 1] = dmy; out.d_means[3 * sg + 2] = dmz;
-    out.d_opacities[sg] = dop;
-    float *dc = out.d_cov + sg * cov_n;
-    if (d.cov_layout == PS_COV_TRIU6) {
+    if (live) {
+        out.d_means[3 * sg + 0] = dmx; out.d_means[3 * sg + 1] = dmy; out.d_means[3 * sg + 2] = dmz;
+        out.d_opacities[sg] = dop;
+        float *dc = out.d_cov + sg * cov_n;
+        if (d.cov_layout == PS_COV_TRIU6) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) dc[i] = dcov[i];
-    } else {
-        dc[0] = dcov[0]; dc[1] = dcov[1]; dc[2] = dcov[2];
-        dc[3] = 0.0f;    dc[4] = dcov[3]; dc[5] = dcov[4];
-        dc[6] = 0.0f;    dc[7] = 0.0f;    dc[8] = dcov[5];
+            for (int i = 0; i < 6; ++i) dc[i] = dcov[i];
+        } else {
+            dc[0] = dcov[0]; dc[1] = dcov[1]; dc[2] = dcov[2];
+            dc[3] = 0.0f;    dc[4] = dcov[3]; dc[5] = dcov[4];
+            dc[6] = 0.0f;    dc[7] = 0.0f;    dc[8] = dcov[5];
+        }
+        if (M == 0) {
+            float *dsh = out.d_sh + sg * 3;
+            dsh[0] = dcol[0]; dsh[1] = dcol[1]; dsh[2] = dcol[2];
+        }
     }
-    if (d.M > 0) {
-        if (!sh_written)
-            for (int i = 0; i < sh_n; ++i) dsh[i] = 0.0f;
-    } else {
-        dsh[0] = dcol[0]; dsh[1] = dcol[1]; dsh[2] = dcol[2];
+    if (M > 0) {
+        // warp-cooperative, coalesced write-out of the 32 staged rows (zeros where nothing was written)
+        const unsigned written = __ballot_sync(0xffffffffu, sh_written);
+        __syncwarp();
+        const int rows = min(32, d.P - g0);
+        if (rows > 0) {
+            const int total = rows * sh_n;
+            float *dst = out.d_sh + ((size_t)scene * d.P + g0) * (size_t)sh_n;
+            const float *wbase = s_dsh + (size_t)warp * 32 * row_stride;
+            const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+            const int nvec = vec_ok ? total / 4 : 0;
+            for (int i = lane; i < nvec; i += 32) {
+                float t[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int e = 4 * i + q, r = e / sh_n, c = e - r * sh_n;
+                    t[q] = ((written >> r) & 1u) ? wbase[r * row_stride + c] : 0.0f;
+                }
+                reinterpret_cast<float4 *>(dst)[i] = make_float4(t[0], t[1], t[2], t[3]);
+            }
+            for (int e = 4 * nvec + lane; e < total; e += 32) {
+                const int r = e / sh_n, c = e - r * sh_n;
+                dst[e] = ((written >> r) & 1u) ? wbase[r * row_stride + c] : 0.0f;
+            }
+        }
     }
 }
 
 int launch_preprocess_backward(const Dims &d, const Inputs &in, const Geom &g, const ViewGrads &vg,
                                const ps_raster_grads &out, cudaStream_t st) {
     dim3 grid((d.P + kPreBwdThreads - 1) / kPreBwdThreads, d.S);
-    k_preprocess_bwd<<<grid, kPreBwdThreads, 0, st>>>(d, in, g, vg, out);
+    const int row_stride = d.M > 0 ? ((3 * d.M) | 1) : 1;
+    const size_t smem = d.M > 0 ? sizeof(float) * kPreBwdThreads * row_stride : 0;
+    static bool attr = false;
+    if (!attr) {
+        PS_CUDA_CHECK(cudaFuncSetAttribute(k_preprocess_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr = true;
+    }
+    k_preprocess_bwd<<<grid, kPreBwdThreads, smem, st>>>(d, in, g, vg, out, row_stride);
     PS_LAUNCH_CHECK("k_preprocess_bwd");
     return PS_OK;
 }

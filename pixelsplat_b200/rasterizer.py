@@ -31,6 +31,7 @@ _capacity_hint: dict[tuple, int] = {}
 _pinned: Optional[Tensor] = None
 _pinned_next = 0
 _PINNED_SLOTS = 256
+_segment_hint: dict[tuple, int] = {}
 
 
 def set_capacity_check(mode: str) -> None:
@@ -43,8 +44,8 @@ def set_capacity_check(mode: str) -> None:
 def _pinned_slot() -> Tensor:
     global _pinned, _pinned_next
     if _pinned is None:
-        _pinned = torch.zeros(_PINNED_SLOTS, dtype=torch.int64).pin_memory()
-    slot = _pinned[_pinned_next:_pinned_next + 1]
+        _pinned = torch.zeros(2 * _PINNED_SLOTS, dtype=torch.int64).pin_memory()
+    slot = _pinned[2 * _pinned_next:2 * _pinned_next + 2]
     _pinned_next = (_pinned_next + 1) % _PINNED_SLOTS
     return slot
 
@@ -77,7 +78,9 @@ class RasterOutputState:
 
     def num_instances(self) -> int:
         self.event.synchronize()
-        return int(self.n_host.item())
+        if self.hint_key is not None:
+            _segment_hint[self.hint_key] = max(int(self.n_host[1].item()), 1)
+        return int(self.n_host[0].item())
 
     def verify(self) -> None:
         if self.verified:
@@ -127,8 +130,8 @@ class RasterOutputState:
         )
 
 
-def _make_desc(S, V, P, M, deg, sh_layout, cov_layout, H, W, capacity, sort_impl) -> _lib.RasterDesc:
-    return _lib.RasterDesc(S, V, P, M, deg, sh_layout, cov_layout, H, W, sort_impl, capacity)
+def _make_desc(S, V, P, M, deg, sh_layout, cov_layout, H, W, capacity, sort_impl, seg_hint=0) -> _lib.RasterDesc:
+    return _lib.RasterDesc(S, V, P, M, deg, sh_layout, cov_layout, H, W, sort_impl, seg_hint, capacity)
 
 
 def _forward_native(means, cov, opac, sh, cams, S, V, P, M, deg, sh_layout, cov_layout, H, W,
@@ -140,7 +143,8 @@ def _forward_native(means, cov, opac, sh, cams, S, V, P, M, deg, sh_layout, cov_
         capacity = max(4096, 3 * S * V * P)
     stream = torch.cuda.current_stream(dev)
     while True:
-        desc = _make_desc(S, V, P, M, deg, sh_layout, cov_layout, H, W, capacity, sort_impl)
+        desc = _make_desc(S, V, P, M, deg, sh_layout, cov_layout, H, W, capacity, sort_impl,
+                          min(_segment_hint.get(key, 0), 1 << 30))
         sz = _lib.sizes(desc)
         geom = torch.empty(sz.geom_bytes, dtype=torch.uint8, device=dev)
         binning = torch.empty(sz.binning_bytes, dtype=torch.uint8, device=dev)

@@ -51,7 +51,7 @@ def test_ctypes_structs_match_the_header(tmp_path):
 
 def test_sizes_layout_and_validation_without_gpu():
     from pixelsplat_b200 import _lib
-    d = _lib.RasterDesc(2, 3, 1000, 25, 4, _lib.PS_SH_3M, _lib.PS_COV_3X3, 70, 50, 0, 12345)
+    d = _lib.RasterDesc(2, 3, 1000, 25, 4, _lib.PS_SH_3M, _lib.PS_COV_3X3, 70, 50, 0, 0, 12345)
     s, lay = _lib.sizes(d), _lib.layout(d)
     vp, tiles = 2 * 3 * 1000, 4 * 5
     assert lay.depth == 0 and lay.radii >= vp * 4 and lay.keys == 0 and lay.keys_alt >= 12345 * 8
@@ -63,15 +63,15 @@ def test_sizes_layout_and_validation_without_gpu():
     for field, bad in (("n_gaussians", 0), ("sh_degree", 5), ("sh_coeffs", 26), ("sh_layout", 7),
                        ("cov_layout", -1), ("height", 0), ("instance_capacity", 0),
                        ("instance_capacity", 1 << 31)):
-        d2 = _lib.RasterDesc(1, 1, 10, 25, 4, 0, 0, 16, 16, 0, 100)
+        d2 = _lib.RasterDesc(1, 1, 10, 25, 4, 0, 0, 16, 16, 0, 0, 100)
         setattr(d2, field, bad)
         with pytest.raises(ValueError, match="PS_ERR_INVALID_ARGUMENT"):
             _lib.sizes(d2)
-    d3 = _lib.RasterDesc(1, 1, 10, 4, 2, 0, 0, 16, 16, 0, 100)    # degree 2 needs 9 coefficients
+    d3 = _lib.RasterDesc(1, 1, 10, 4, 2, 0, 0, 16, 16, 0, 0, 100)    # degree 2 needs 9 coefficients
     with pytest.raises(ValueError, match="needs 9 coefficients"):
         _lib.sizes(d3)
     # NULL pointers are rejected before anything is launched
-    d4 = _lib.RasterDesc(1, 1, 10, 25, 4, 0, 0, 16, 16, 0, 100)
+    d4 = _lib.RasterDesc(1, 1, 10, 25, 4, 0, 0, 16, 16, 0, 0, 100)
     rc = _lib.lib.ps_raster_forward(ctypes.byref(d4), None, None, None, None, None, None)
     assert rc == 1 and b"NULL" in _lib.lib.ps_last_error()
 
