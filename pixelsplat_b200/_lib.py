@@ -54,6 +54,16 @@ class RasterLayout(ctypes.Structure):
         "tile_start", "tile_cursor", "n_instances", "keys", "keys_alt", "final_T", "n_contrib")]
 
 
+class EpipolarDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "batch", "views", "grid_h", "grid_w", "samples", "channels", "heads", "pe_dim")]
+
+
+class EpipolarInputs(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        "features", "segments", "valid", "rel_disparity", "q_feat", "q_pe", "bias")]
+
+
 class RasterGrads(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
         "d_means", "d_cov", "d_opacities", "d_sh", "d_means2d")]
@@ -61,7 +71,8 @@ class RasterGrads(ctypes.Structure):
 
 EXPORTS = ("ps_version", "ps_last_error", "ps_raster_sizes_query", "ps_raster_layout_query",
            "ps_raster_forward", "ps_raster_backward", "ps_camera_setup", "ps_launch_count",
-           "ps_timing_enable", "ps_timing_read")
+           "ps_timing_enable", "ps_timing_read", "ps_epipolar_geometry",
+           "ps_epipolar_attention_forward", "ps_epipolar_attention_backward")
 
 
 class NativeLibraryMissing(ImportError):
@@ -91,6 +102,12 @@ def _load() -> ctypes.CDLL:
     lib.ps_timing_enable.restype = None
     lib.ps_timing_read.argtypes = [ctypes.POINTER(ctypes.c_float)]
     lib.ps_timing_read.restype = ctypes.c_int
+    lib.ps_epipolar_geometry.argtypes = [ctypes.c_int32] * 5 + [ctypes.c_void_p] * 9
+    lib.ps_epipolar_geometry.restype = ctypes.c_int
+    lib.ps_epipolar_attention_forward.argtypes = [P(EpipolarDesc), P(EpipolarInputs)] + [ctypes.c_void_p] * 5
+    lib.ps_epipolar_attention_forward.restype = ctypes.c_int
+    lib.ps_epipolar_attention_backward.argtypes = [P(EpipolarDesc), P(EpipolarInputs)] + [ctypes.c_void_p] * 10
+    lib.ps_epipolar_attention_backward.restype = ctypes.c_int
     for f in ("ps_raster_sizes_query", "ps_raster_layout_query", "ps_raster_forward", "ps_raster_backward"):
         getattr(lib, f).restype = ctypes.c_int
     return lib
