@@ -86,16 +86,23 @@ __device__ __forceinline__ float warp_add(float v) {
     return v;
 }
 
-// PE(rd)[2k] = sin(2 pi rd 2^k), [2k+1] = cos(...)  (positional_encoding.py:14-33, layout "(d f p)").
-// rd * 2^(k+1) is exact in fp32 and sincospif reduces its argument exactly, so the encoding is
-// accurate to ~1 ulp of the *phase* -- the reference's fp32 `sin(rd * (2 pi 2^k) + phi)` is not.
+// PE(rd)[2k] = sin(f_k rd), [2k+1] = sin(f_k rd + pi/2), layout "(d f p)"
+// (positional_encoding.py:14-33).  The reference's frequency buffer is float32(2 pi) * 2^k, i.e.
+// 2 pi (1 + delta) 2^k with delta = 2.78e-8 -- a phase shift of up to 9e-5 rad at k = 9 that is
+// part of its semantics (the buffer is non-persistent, so every checkpoint gets it), so it is
+// reproduced: phase/pi = u (1 + delta), u = rd 2^(k+1) formed exactly, reduced exactly mod 2, and
+// evaluated with sincospif.  (The reference's own fp32 `sin(rd * f_k + phi)` rounds the product,
+// up to 2e-4 rad at k = 9; this evaluation is closer to its float64 result.)
 __device__ __forceinline__ void positional_encoding(float rd, int npe, float (&pe)[kMaxPE]) {
+    constexpr float kTwoPiF32Excess = 2.7827534e-8f;   // float32(2 pi) / (2 pi) - 1
     float scale = 2.0f;
 #pragma unroll
     for (int k = 0; k < kMaxPE / 2; ++k) {
         if (2 * k < npe) {
             float s, c;
-            sincospif(rd * scale, &s, &c);
+            const float u = rd * scale;
+            const float ur = u - 2.0f * floorf(0.5f * u);
+            sincospif(ur + u * kTwoPiF32Excess, &s, &c);
             pe[2 * k] = s;
             pe[2 * k + 1] = c;
             scale *= 2.0f;
@@ -493,7 +500,7 @@ extern "C" PS_API int ps_epipolar_attention_forward(const ps_epipolar_desc *d, c
     int rc = epi_check(d);
     if (rc) return rc;
     if (!in || !in->features || !in->segments || !in->valid || !in->rel_disparity || !in->q_feat ||
-        (d->pe_dim > 0 && !in->q_pe) || !z || !e || !lse) {
+        (d->pe_dim > 0 && (!in->q_pe || !e)) || !z || !lse) {
         set_error("ps_epipolar_attention_forward: a required pointer is NULL");
         return PS_ERR_INVALID_ARGUMENT;
     }
@@ -515,7 +522,7 @@ extern "C" PS_API int ps_epipolar_attention_backward(const ps_epipolar_desc *d, 
     int rc = epi_check(d);
     if (rc) return rc;
     if (!in || !in->features || !in->segments || !in->valid || !in->rel_disparity || !in->q_feat || !lse ||
-        !dz || !de || !d_row || !dq_feat || !dq_pe || !dfeatures) {
+        !dz || (d->pe_dim > 0 && (!de || !dq_pe)) || !d_row || !dq_feat || !dfeatures) {
         set_error("ps_epipolar_attention_backward: a required pointer is NULL");
         return PS_ERR_INVALID_ARGUMENT;
     }
