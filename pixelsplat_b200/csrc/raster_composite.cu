@@ -40,10 +40,15 @@ struct StageBuf {
     float4 rgb[kStage];
 };
 
+// The staged conic is pre-multiplied so that  power * log2(e) = qa dx^2 + qc dy^2 + qb dx dy
+// (one MUFU.EX2, no extra multiply, per evaluation); the sign test `power > 0` is unchanged.
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
 __device__ __forceinline__ void stage_entry(StageBuf &s, int slot, const Geom &geo, size_t base, uint32_t g) {
     const float4 co = geo.conic_opacity[base + g];
     s.xy[slot] = geo.xy[base + g];
-    s.co[slot] = co;
+    s.co[slot] = make_float4(-0.5f * kLog2e * co.x, -kLog2e * co.y, -0.5f * kLog2e * co.z, co.w);
     s.rgb[slot] = geo.rgb[base + g];
     s.ext[slot] = alpha_extent(co);
 }
@@ -86,24 +91,45 @@ k_composite_fwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                     hit = (c.x + e.x >= rx0) && (c.x - e.x <= rx1) && (c.y + e.y >= ry0) && (c.y - e.y <= ry1);
                 }
                 uint32_t mask = __ballot_sync(0xffffffffu, hit);
+                // two entries per iteration: their power / exp evaluations are independent, only
+                // the transmittance update chains (the warp has few peers to hide latency behind:
+                // a 256x256 view is just 2048 warps on 148 SMs)
                 while (mask) {
-                    const int bpos = __ffs(mask) - 1;
+                    const int b0 = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    if (done) continue;
-                    const float2 exy = s.xy[jb + bpos];
-                    const float4 eco = s.co[jb + bpos];
-                    const float dx = exy.x - px, dy = exy.y - py;
-                    const float power = -0.5f * (eco.x * dx * dx + eco.z * dy * dy) - eco.y * dx * dy;
-                    if (power > 0.0f) continue;
-                    const float alpha = fminf(0.99f, eco.w * __expf(power));
-                    if (alpha < kAlphaMin) continue;
-                    const float test_T = T * (1.0f - alpha);
-                    if (test_T < 0.0001f) { done = true; continue; }
-                    const float w = alpha * T;
-                    const float4 ergb = s.rgb[jb + bpos];
-                    Cr += ergb.x * w; Cg += ergb.y * w; Cb += ergb.z * w;
-                    T = test_T;
-                    last = round0 + jb + (uint32_t)bpos + 1u;
+                    const bool two = mask != 0;
+                    const int b1 = two ? __ffs(mask) - 1 : b0;
+                    mask &= mask - 1;
+                    const float2 xy0 = s.xy[jb + b0], xy1 = s.xy[jb + b1];
+                    const float4 co0 = s.co[jb + b0], co1 = s.co[jb + b1];
+                    const float4 c0 = s.rgb[jb + b0], c1 = s.rgb[jb + b1];
+                    const float dx0 = xy0.x - px, dy0 = xy0.y - py, dx1 = xy1.x - px, dy1 = xy1.y - py;
+                    const float p0 = co0.x * dx0 * dx0 + co0.z * dy0 * dy0 + co0.y * dx0 * dy0;
+                    const float p1 = co1.x * dx1 * dx1 + co1.z * dy1 * dy1 + co1.y * dx1 * dy1;
+                    const float alpha0 = fminf(0.99f, co0.w * exp2f(p0));
+                    const float alpha1 = fminf(0.99f, co1.w * exp2f(p1));
+                    {
+                        const bool contrib = !done && !(p0 > 0.0f) && !(alpha0 < kAlphaMin);
+                        const float test_T = T * (1.0f - alpha0);
+                        const bool stop = contrib && (test_T < 0.0001f);
+                        const bool blend = contrib && !stop;
+                        const float w = blend ? alpha0 * T : 0.0f;
+                        Cr += c0.x * w; Cg += c0.y * w; Cb += c0.z * w;
+                        T = blend ? test_T : T;
+                        last = blend ? round0 + jb + (uint32_t)b0 + 1u : last;
+                        done = done || stop;
+                    }
+                    {
+                        const bool contrib = two && !done && !(p1 > 0.0f) && !(alpha1 < kAlphaMin);
+                        const float test_T = T * (1.0f - alpha1);
+                        const bool stop = contrib && (test_T < 0.0001f);
+                        const bool blend = contrib && !stop;
+                        const float w = blend ? alpha1 * T : 0.0f;
+                        Cr += c1.x * w; Cg += c1.y * w; Cb += c1.z * w;
+                        T = blend ? test_T : T;
+                        last = blend ? round0 + jb + (uint32_t)b1 + 1u : last;
+                        done = done || stop;
+                    }
                 }
                 warp_done = __all_sync(0xffffffffu, done);
                 if (warp_done) break;
@@ -155,48 +181,45 @@ struct PixelState {
     float T, acc_r, acc_g, acc_b, last_alpha, lc_r, lc_g, lc_b;
 };
 
+// Straight-line (predicated, no divergent branches): on average only ~10 of a warp's 32 pixels
+// take a given entry, but the warp executes the whole body anyway, and the reconvergence
+// bookkeeping of a branchy version was 13 % of the issued instructions (profiles/r01_*).
 __device__ __forceinline__ bool pixel_bwd(bool in_range, const float2 exy, const float4 eco, const float4 ergb,
                                           float px, float py, float dpr, float dpg, float dpb, float T_final,
                                           float bg_dot, float ddelx_dx, float ddely_dy, PixelState &st,
                                           float *g, float &op) {
-    bool active = in_range;
-    float dx = 0.0f, dy = 0.0f, G = 0.0f, alpha = 0.0f;
-    if (active) {
-        dx = exy.x - px; dy = exy.y - py;
-        const float power = -0.5f * (eco.x * dx * dx + eco.z * dy * dy) - eco.y * dx * dy;
-        active = !(power > 0.0f);
-        if (active) {
-            G = __expf(power);
-            alpha = fminf(0.99f, eco.w * G);
-            active = !(alpha < kAlphaMin);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) g[k] = 0.0f;
-    op = 0.0f;
-    if (active) {
-        st.T = st.T / (1.0f - alpha);
-        const float dchannel_dcolor = alpha * st.T;
-        st.acc_r = st.last_alpha * st.lc_r + (1.0f - st.last_alpha) * st.acc_r;
-        st.acc_g = st.last_alpha * st.lc_g + (1.0f - st.last_alpha) * st.acc_g;
-        st.acc_b = st.last_alpha * st.lc_b + (1.0f - st.last_alpha) * st.acc_b;
-        st.lc_r = ergb.x; st.lc_g = ergb.y; st.lc_b = ergb.z;
-        float dL_dalpha = (ergb.x - st.acc_r) * dpr + (ergb.y - st.acc_g) * dpg + (ergb.z - st.acc_b) * dpb;
-        g[5] = dchannel_dcolor * dpr; g[6] = dchannel_dcolor * dpg; g[7] = dchannel_dcolor * dpb;
-        dL_dalpha *= st.T;
-        st.last_alpha = alpha;
-        dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot;
-        const float dL_dG = eco.w * dL_dalpha;
-        const float gdx = G * dx, gdy = G * dy;
-        const float dG_ddelx = -gdx * eco.x - gdy * eco.y;
-        const float dG_ddely = -gdy * eco.z - gdx * eco.y;
-        g[0] = dL_dG * dG_ddelx * ddelx_dx;
-        g[1] = dL_dG * dG_ddely * ddely_dy;
-        g[2] = -0.5f * gdx * dx * dL_dG;
-        g[3] = -0.5f * gdx * dy * dL_dG;
-        g[4] = -0.5f * gdy * dy * dL_dG;
-        op = G * dL_dalpha;
-    }
+    const float dx = exy.x - px, dy = exy.y - py;
+    const float p2 = eco.x * dx * dx + eco.z * dy * dy + eco.y * dx * dy;   // power * log2(e)
+    const float G = exp2f(p2);
+    const float alpha = fminf(0.99f, eco.w * G);
+    const bool active = in_range && !(p2 > 0.0f) && !(alpha < kAlphaMin);
+    const float a = active ? alpha : 0.0f;
+    const float rcp = __fdividef(1.0f, 1.0f - a);                              // 1 when inactive
+    st.T = st.T * rcp;
+    const float dchannel_dcolor = a * st.T;
+    const float la = st.last_alpha, one_m = 1.0f - la;
+    const float nr = la * st.lc_r + one_m * st.acc_r, ng = la * st.lc_g + one_m * st.acc_g,
+                nb = la * st.lc_b + one_m * st.acc_b;
+    st.acc_r = active ? nr : st.acc_r; st.acc_g = active ? ng : st.acc_g; st.acc_b = active ? nb : st.acc_b;
+    st.lc_r = active ? ergb.x : st.lc_r; st.lc_g = active ? ergb.y : st.lc_g; st.lc_b = active ? ergb.z : st.lc_b;
+    st.last_alpha = active ? alpha : la;
+    float dL_dalpha = (ergb.x - nr) * dpr + (ergb.y - ng) * dpg + (ergb.z - nb) * dpb;
+    dL_dalpha = dL_dalpha * st.T - T_final * rcp * bg_dot;
+    dL_dalpha = active ? dL_dalpha : 0.0f;
+    g[5] = dchannel_dcolor * dpr; g[6] = dchannel_dcolor * dpg; g[7] = dchannel_dcolor * dpb;
+    const float dL_dG = eco.w * dL_dalpha;
+    const float Gs = active ? G : 0.0f;   // exp2 of a non-PSD conic may overflow: keep 0 * inf out
+    const float gdx = Gs * dx, gdy = Gs * dy;
+    // dG/d(delta) = -G (A dx + B dy) with A = -2 qa / log2e, B = -qb / log2e
+    const float dG_ddelx = kLn2 * (2.0f * eco.x * gdx + eco.y * gdy);
+    const float dG_ddely = kLn2 * (2.0f * eco.z * gdy + eco.y * gdx);
+    g[0] = dL_dG * dG_ddelx * ddelx_dx;
+    g[1] = dL_dG * dG_ddely * ddely_dy;
+    const float h = -0.5f * dL_dG;
+    g[2] = h * gdx * dx;
+    g[3] = h * gdx * dy;
+    g[4] = h * gdy * dy;
+    op = Gs * dL_dalpha;
     return active;
 }
 
@@ -207,7 +230,11 @@ k_composite_bwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                 ViewGrads vg) {
     __shared__ StageBuf s;
     __shared__ uint32_t s_g[kStage];
-    __shared__ float s_acc[kStage][9];  // mean2d.xy, conic.xyz, color.rgb, opacity
+    // Per-warp private gradient accumulators [warp][entry][9 (+1 pad)] in dynamic shared memory:
+    // shared-memory float atomics compile to CAS loops, and 8 warps hammering the same entry
+    // serialised (they were 1/6 of this kernel's stall samples).
+    extern __shared__ float s_acc_all[];
+    float(*s_acc)[10] = reinterpret_cast<float(*)[10]>(s_acc_all) + (size_t)(threadIdx.x >> 5) * kStage;
     __shared__ uint32_t s_max_last;
     const int vid = blockIdx.y, tile = blockIdx.x;
     const int tx = tile % d.gx, ty = tile / d.gx;
@@ -255,8 +282,7 @@ k_composite_bwd(Dims d, Geom geo, const float *__restrict__ bg_all,
             stage_entry(s, tid, geo, gbase, g);
             s_g[tid] = g;
         }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) s_acc[tid][k] = 0.0f;
+        for (int i = tid; i < (kCompThreads / 32) * kStage * 10; i += kCompThreads) s_acc_all[i] = 0.0f;
         __syncthreads();
         for (uint32_t jb = 0; jb < n_here; jb += 32) {
             const uint32_t j = jb + lane;
@@ -286,24 +312,31 @@ k_composite_bwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                 const float tot = transpose_reduce16(v, lane);
                 op0 = warp_sum(op0);
                 op1 = warp_sum(op1);
+                // this warp's private copy: plain read-modify-write, no other warp touches it
                 if ((lane & 1) == 0) {
                     const int vi = lane >> 1;               // 0..15
                     const bool second = vi >= 8;
-                    if (second ? (any1 != 0u) : (any0 != 0u))
-                        atomicAdd(&s_acc[second ? j1 : j0][vi & 7], tot);
+                    if (second ? (two && any1 != 0u) : (any0 != 0u)) s_acc[second ? j1 : j0][vi & 7] += tot;
                 } else if (lane == 1) {
-                    if (any0) atomicAdd(&s_acc[j0][8], op0);
+                    if (any0) s_acc[j0][8] += op0;
                 } else if (lane == 3) {
-                    if (any1) atomicAdd(&s_acc[j1][8], op1);
+                    if (two && any1) s_acc[j1][8] += op1;
                 }
+                __syncwarp();
             }
         }
         __syncthreads();
         if ((uint32_t)tid < n_here) {
-            const float *a = s_acc[tid];
+            float a[9];
             bool any = false;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) any |= (a[k] != 0.0f);
+            for (int k = 0; k < 9; ++k) {
+                float t = 0.0f;
+#pragma unroll
+                for (int w8 = 0; w8 < kCompThreads / 32; ++w8) t += s_acc_all[((size_t)w8 * kStage + tid) * 10 + k];
+                a[k] = t;
+                any |= (t != 0.0f);
+            }
             if (any) {
                 const size_t o = gbase + s_g[tid];
                 float *m = reinterpret_cast<float *>(vg.d_mean2d + o);
@@ -333,7 +366,13 @@ int launch_composite_backward(const Dims &d, const Inputs &in, const Geom &g,
                               const uint32_t *n_contrib, const float *d_color, const ViewGrads &vg,
                               cudaStream_t st) {
     dim3 grid(d.tiles, d.S * d.V);
-    k_composite_bwd<<<grid, kCompThreads, 0, st>>>(d, g, in.bg, keys, final_T, n_contrib, d_color, vg);
+    const size_t acc_bytes = sizeof(float) * (kCompThreads / 32) * kStage * 10;
+    static bool attr = false;
+    if (!attr) {
+        PS_CUDA_CHECK(cudaFuncSetAttribute(k_composite_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
+        attr = true;
+    }
+    k_composite_bwd<<<grid, kCompThreads, acc_bytes, st>>>(d, g, in.bg, keys, final_T, n_contrib, d_color, vg);
     PS_LAUNCH_CHECK("k_composite_bwd");
     return PS_OK;
 }
