@@ -128,13 +128,13 @@ __global__ void __launch_bounds__(kSortThreads)
 k_tile_sort(const uint32_t *__restrict__ tile_start, const uint32_t *__restrict__ tile_count,
             const long long *__restrict__ n_instances, long long capacity,
             unsigned long long *__restrict__ keys, unsigned long long *__restrict__ keys_alt,
-            int smem_cap, int id_bits) {
+            int smem_cap, int min_n, int id_bits) {
     static_assert(kSortThreads == 256, "one thread per 8-bit digit");
     extern __shared__ __align__(16) unsigned char s_raw[];
     if (*n_instances > capacity) return;
     const int seg = blockIdx.x;
     const int n = (int)tile_count[seg];
-    if (n < 2) return;
+    if (n < 2 || n <= min_n) return;   // short segments were sorted by the bitonic launch
     const uint32_t s0 = tile_start[seg];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -228,6 +228,44 @@ k_tile_sort(const uint32_t *__restrict__ tile_start, const uint32_t *__restrict_
     }
 }
 
+// ---------------------------------------------------------------- per-tile bitonic sort
+// For the common case (a few thousand keys per tile) a bitonic network over the full 64-bit
+// key beats the radix sort by ~8x: no histograms, no atomics, ~log^2(n)/2 barrier-separated
+// compare-exchange steps, and it is oblivious to ties.  One CTA per (view, tile); segments
+// longer than `cap` (a power of two, chosen by the host from the previous call's longest
+// segment) are left to the radix kernel.
+constexpr int kBitonicThreads = 512;
+
+__global__ void __launch_bounds__(kBitonicThreads)
+k_tile_sort_bitonic(const uint32_t *__restrict__ tile_start, const uint32_t *__restrict__ tile_count,
+                    const long long *__restrict__ n_instances, long long capacity,
+                    unsigned long long *__restrict__ keys, int cap) {
+    extern __shared__ __align__(16) unsigned long long s_keys[];
+    if (*n_instances > capacity) return;
+    const int seg = blockIdx.x;
+    const int n = (int)tile_count[seg];
+    if (n < 2 || n > cap) return;
+    const uint32_t s0 = tile_start[seg];
+    int n_pad = 2;
+    while (n_pad < n) n_pad <<= 1;
+    for (int i = threadIdx.x; i < n_pad; i += kBitonicThreads) s_keys[i] = i < n ? keys[s0 + i] : ~0ull;
+    __syncthreads();
+    const int half = n_pad >> 1;
+    for (int k = 2; k <= n_pad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < half; t += kBitonicThreads) {
+                const int i = 2 * t - (t & (j - 1));      // bit j of i is clear
+                const int p = i + j;
+                const unsigned long long a = s_keys[i], b = s_keys[p];
+                const bool up = (i & k) == 0;
+                if ((a > b) == up) { s_keys[i] = b; s_keys[p] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += kBitonicThreads) keys[s0 + i] = s_keys[i];
+}
+
 static size_t sort_smem_bytes(int cap) {
     return sizeof(uint32_t) * (kSortWarps * 256 + 256 + 16) + sizeof(unsigned long long) * 2 * (size_t)cap;
 }
@@ -283,14 +321,35 @@ int launch_binning(const Dims &d, const Geom &g, unsigned long long *keys,
                                            (int)sort_smem_bytes(12288)));
         attr_set = true;
     }
-    int cap = 2048;   // no hint: typical 256x256 tiles fit; longer ones take the HBM ping-pong
+    // Bitonic network in shared memory for segments up to 8192 keys (power-of-two capacity picked
+    // from the hint, with 25 % head-room); the radix kernel then only does work for segments the
+    // bitonic launch skipped (its CTAs exit at once otherwise).
+    int bitonic_cap = 2048;
     if (segment_hint > 0) {
-        cap = kSortCaps[4];
-        for (int i = 4; i >= 0; --i) if (segment_hint <= kSortCaps[i]) cap = kSortCaps[i];
+        const long long want = (long long)segment_hint + segment_hint / 4;
+        while (bitonic_cap < want && bitonic_cap < 8192) bitonic_cap <<= 1;
     }
-    k_tile_sort<<<n_seg, kSortThreads, sort_smem_bytes(cap), st>>>(
-        g.tile_start, g.tile_count, g.n_instances, d.capacity, keys, keys_alt, cap, id_bits);
-    PS_LAUNCH_CHECK("k_tile_sort");
+    static bool battr = false;
+    if (!battr) {
+        PS_CUDA_CHECK(cudaFuncSetAttribute(k_tile_sort_bitonic, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(8192 * sizeof(unsigned long long))));
+        battr = true;
+    }
+    k_tile_sort_bitonic<<<n_seg, kBitonicThreads, bitonic_cap * sizeof(unsigned long long), st>>>(
+        g.tile_start, g.tile_count, g.n_instances, d.capacity, keys, bitonic_cap);
+    PS_LAUNCH_CHECK("k_tile_sort_bitonic");
+    const bool may_exceed = segment_hint <= 0 || (long long)segment_hint + segment_hint / 4 > bitonic_cap;
+    if (may_exceed || sort_impl == 2) {
+        k_tile_sort<<<n_seg, kSortThreads, sort_smem_bytes(4096), st>>>(
+            g.tile_start, g.tile_count, g.n_instances, d.capacity, keys, keys_alt, 4096, bitonic_cap, id_bits);
+        PS_LAUNCH_CHECK("k_tile_sort");
+    } else {
+        // hint says everything fits; still guarantee correctness if the hint was stale: a tiny
+        // grid re-checks and sorts any oversize segment
+        k_tile_sort<<<n_seg, kSortThreads, sort_smem_bytes(1024), st>>>(
+            g.tile_start, g.tile_count, g.n_instances, d.capacity, keys, keys_alt, 1024, bitonic_cap, id_bits);
+        PS_LAUNCH_CHECK("k_tile_sort");
+    }
     return PS_OK;
 }
 

@@ -54,6 +54,15 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
             const float2 t = vis ? vgr.d_mean2d[vg] : make_float2(0.0f, 0.0f);
             m2[0] = t.x; m2[1] = t.y; m2[2] = 0.0f;
         }
+        // single-view calls: the warp's SH coefficients are staged (coalesced) into the same
+        // shared rows that will receive the gradient; each coefficient is read just before its
+        // slot is overwritten
+        const bool staged_in_place = M > 0 && d.V == 1;
+        if (staged_in_place && __any_sync(0xffffffffu, vis)) {
+            stage_sh_rows(in.sh + ((size_t)scene * d.P + g0) * (size_t)sh_n, s_dsh + (size_t)warp * 32 * row_stride,
+                          min(32, d.P - g0), sh_n, row_stride, lane);
+            __syncwarp();
+        }
         if (!vis) continue;
         const float *__restrict__ vm = in.view + 16 * vid;
         const float *__restrict__ pm = in.proj + 16 * vid;
@@ -135,9 +144,10 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
                     const int idx = sh_index(layout, M, k, ch);
+                    const float coef = staged_in_place ? row[idx] : __ldg(sh + idx);
                     const float val = Y * dl[ch];
                     row[idx] = first ? val : row[idx] + val;
-                    const float cd = __ldg(sh + idx) * dl[ch];
+                    const float cd = coef * dl[ch];
                     dLdx += Yx * cd; dLdy += Yy * cd; dLdz += Yz * cd;
                 }
             });

@@ -1,0 +1,67 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: scene sharding, disjoint seeds,
+max-over-ranks timing, bucketed gradient all-reduce with unused parameters."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pixelsplat_b200 import parallel
+
+
+def test_shard_range_is_a_balanced_partition():
+    for n in (0, 1, 7, 8, 28, 29):
+        for world in (1, 2, 3, 8):
+            parts = [parallel.shard_range(n, r, world) for r in range(world)]
+            assert [i for p in parts for i in p] == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    seeds = {parallel.scene_seed(0, r, i) for r in range(8) for i in range(7)}
+    assert len(seeds) == 56
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    r, w, _ = parallel.init_distributed("gloo")
+    assert (r, w) == (rank, world)
+    # timing: max over ranks
+    t = parallel.max_over_ranks(1.0 + rank)
+    # gradients: rank-dependent grads, one unused parameter on rank 1, tiny buckets
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    extra = torch.nn.Parameter(torch.ones(5))
+    x = torch.full((3, 8), float(rank + 1))
+    loss = model(x).sum() + (extra.sum() * 2 if rank == 0 else 0)
+    loss.backward()
+    params = list(model.parameters()) + [extra]
+    local = [None if p.grad is None else p.grad.clone() for p in params]
+    n_coll = parallel.allreduce_gradients(params, bucket_bytes=256)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local)
+    ok = True
+    for i, p in enumerate(params):
+        parts = [g[i] if g[i] is not None else torch.zeros_like(p) for g in gathered]
+        ok &= torch.allclose(p.grad, sum(parts) / world, atol=1e-6)
+    out[rank] = (t, n_coll, bool(ok), parallel.aggregate_throughput(10.0, t, world))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gloo_world2_collectives():
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+        res = dict(out)
+    assert res[0][0] == res[1][0] == 2.0                 # max over ranks
+    assert res[0][1] == res[1][1] and res[0][1] >= 2     # several buckets
+    assert res[0][2] and res[1][2]
+    assert res[0][3] == pytest.approx(10.0)              # 2 ranks x 10 units / 2 s
