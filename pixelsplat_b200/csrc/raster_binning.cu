@@ -250,9 +250,18 @@ k_tile_sort_bitonic(const uint32_t *__restrict__ tile_start, const uint32_t *__r
     while (n_pad < n) n_pad <<= 1;
     for (int i = threadIdx.x; i < n_pad; i += kBitonicThreads) s_keys[i] = i < n ? keys[s0 + i] : ~0ull;
     __syncthreads();
+    // Each warp owns a contiguous chunk of n_pad / 16 keys: every compare-exchange step whose
+    // stride is below the chunk size stays inside one warp and needs only __syncwarp; the CTA
+    // barrier is paid for the few long-stride steps (10 of 66 at 2048 keys).
+    constexpr int kWarps = kBitonicThreads / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk = max(n_pad / kWarps, 2);          // power of two
+    const int warps_used = n_pad / chunk;              // < kWarps only for tiny segments
     const int half = n_pad >> 1;
     for (int k = 2; k <= n_pad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
+        int j = k >> 1;
+        const bool had_global = j >= chunk;
+        for (; j >= chunk; j >>= 1) {
             for (int t = threadIdx.x; t < half; t += kBitonicThreads) {
                 const int i = 2 * t - (t & (j - 1));      // bit j of i is clear
                 const int p = i + j;
@@ -262,6 +271,21 @@ k_tile_sort_bitonic(const uint32_t *__restrict__ tile_start, const uint32_t *__r
             }
             __syncthreads();
         }
+        if (warp < warps_used) {
+            const int base = warp * chunk;
+            for (; j > 0; j >>= 1) {
+                for (int t = lane; t < (chunk >> 1); t += 32) {
+                    const int i = base + 2 * t - (t & (j - 1));
+                    const int p = i + j;
+                    const unsigned long long a = s_keys[i], b = s_keys[p];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { s_keys[i] = b; s_keys[p] = a; }
+                }
+                __syncwarp();
+            }
+        }
+        // the next k's long-stride steps (or the final copy-out) read other warps' chunks
+        if (had_global || 2 * k > chunk) __syncthreads();
     }
     for (int i = threadIdx.x; i < n; i += kBitonicThreads) keys[s0 + i] = s_keys[i];
 }

@@ -133,19 +133,42 @@ __device__ __forceinline__ void stage_sh_rows(const float *__restrict__ src, flo
                                               int row_stride, int lane) {
     const int total = rows * sh_n;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
-    const int nvec = vec_ok ? total >> 2 : 0;
-    for (int i = lane; i < nvec; i += 32) {
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + i);
-        const float t[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int e = 4 * i + q, r = e / sh_n;
-            dst[r * row_stride + (e - r * sh_n)] = t[q];
-        }
+    if (row_stride == sh_n) {
+        // odd row length (M = 1, 9, 25): rows are already conflict-free, the copy is linear
+        const int nvec = vec_ok ? total >> 2 : 0;
+        for (int i = lane; i < nvec; i += 32)
+            reinterpret_cast<float4 *>(dst)[i] = __ldg(reinterpret_cast<const float4 *>(src) + i);
+        for (int e = 4 * nvec + lane; e < total; e += 32) dst[e] = __ldg(src + e);
+        return;
     }
-    for (int e = 4 * nvec + lane; e < total; e += 32) {
-        const int r = e / sh_n;
-        dst[r * row_stride + (e - r * sh_n)] = __ldg(src + e);
+    // even row length: pad each row by one word; (row, column) advance incrementally (no division)
+    int e = lane, r = e / sh_n, c = e - r * sh_n;
+    const int step_r = 32 / sh_n, step_c = 32 - step_r * sh_n;
+    for (; e < total; e += 32) {
+        dst[r * row_stride + c] = __ldg(src + e);
+        r += step_r; c += step_c;
+        if (c >= sh_n) { c -= sh_n; ++r; }
+    }
+}
+
+// Inverse of stage_sh_rows: one contiguous, coalesced run of rows*sh_n floats back to global.
+__device__ __forceinline__ void unstage_sh_rows(const float *src, float *__restrict__ dst, int rows, int sh_n,
+                                                int row_stride, int lane) {
+    const int total = rows * sh_n;
+    if (row_stride == sh_n) {
+        const bool vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+        const int nvec = vec_ok ? total >> 2 : 0;
+        for (int i = lane; i < nvec; i += 32)
+            reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(src)[i];
+        for (int e = 4 * nvec + lane; e < total; e += 32) dst[e] = src[e];
+        return;
+    }
+    int e = lane, r = e / sh_n, c = e - r * sh_n;
+    const int step_r = 32 / sh_n, step_c = 32 - step_r * sh_n;
+    for (; e < total; e += 32) {
+        dst[e] = src[r * row_stride + c];
+        r += step_r; c += step_c;
+        if (c >= sh_n) { c -= sh_n; ++r; }
     }
 }
 

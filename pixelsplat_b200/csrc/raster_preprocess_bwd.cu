@@ -185,37 +185,22 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
         }
     }
     if (M > 0) {
-        // warp-cooperative, coalesced write-out of the 32 staged rows (zeros where nothing was written)
-        const unsigned written = __ballot_sync(0xffffffffu, sh_written);
+        // rows that received nothing (culled in every view) are zero-filled by their own lane, then
+        // the warp writes its 32 rows out as one contiguous coalesced run
+        if (!sh_written)
+            for (int i = 0; i < sh_n; ++i) row[i] = 0.0f;
         __syncwarp();
         const int rows = min(32, d.P - g0);
-        if (rows > 0) {
-            const int total = rows * sh_n;
-            float *dst = out.d_sh + ((size_t)scene * d.P + g0) * (size_t)sh_n;
-            const float *wbase = s_dsh + (size_t)warp * 32 * row_stride;
-            const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-            const int nvec = vec_ok ? total / 4 : 0;
-            for (int i = lane; i < nvec; i += 32) {
-                float t[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int e = 4 * i + q, r = e / sh_n, c = e - r * sh_n;
-                    t[q] = ((written >> r) & 1u) ? wbase[r * row_stride + c] : 0.0f;
-                }
-                reinterpret_cast<float4 *>(dst)[i] = make_float4(t[0], t[1], t[2], t[3]);
-            }
-            for (int e = 4 * nvec + lane; e < total; e += 32) {
-                const int r = e / sh_n, c = e - r * sh_n;
-                dst[e] = ((written >> r) & 1u) ? wbase[r * row_stride + c] : 0.0f;
-            }
-        }
+        if (rows > 0)
+            unstage_sh_rows(s_dsh + (size_t)warp * 32 * row_stride,
+                            out.d_sh + ((size_t)scene * d.P + g0) * (size_t)sh_n, rows, sh_n, row_stride, lane);
     }
 }
 
 int launch_preprocess_backward(const Dims &d, const Inputs &in, const Geom &g, const ViewGrads &vg,
                                const ps_raster_grads &out, cudaStream_t st) {
     dim3 grid((d.P + kPreBwdThreads - 1) / kPreBwdThreads, d.S);
-    const int row_stride = d.M > 0 ? ((3 * d.M) | 1) : 1;
+    const int row_stride = d.M > 0 ? ((3 * d.M) | 1) : 1;   // odd word count: conflict-free per-lane rows
     const size_t smem = d.M > 0 ? sizeof(float) * kPreBwdThreads * row_stride : 0;
     static bool attr = false;
     if (!attr) {

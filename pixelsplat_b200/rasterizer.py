@@ -77,13 +77,21 @@ class RasterOutputState:
                                 self.binning.numel(), self.image.data_ptr(), self.image.numel())
 
     def num_instances(self) -> int:
-        self.event.synchronize()
+        """Blocks until the forward's instance count has reached the host.  For a forward that was
+        captured into a CUDA graph there is no event: the caller synchronises after a replay."""
+        if self.event is not None:
+            self.event.synchronize()
         if self.hint_key is not None:
             _segment_hint[self.hint_key] = max(int(self.n_host[1].item()), 1)
         return int(self.n_host[0].item())
 
     def verify(self) -> None:
+        """Raises if the binning overflowed its buffer.  Inside a CUDA-graph capture nothing can be
+        waited on, so the check is skipped there: call `verify()` again after replaying and
+        synchronising (bench.py does)."""
         if self.verified:
+            return
+        if self.event is None and torch.cuda.is_current_stream_capturing():
             return
         n = self.num_instances()
         if n > self.desc.instance_capacity:
@@ -163,6 +171,13 @@ def _forward_native(means, cov, opac, sh, cams, S, V, P, M, deg, sh_layout, cov_
                                         _ptr(color), _ptr(radii), ctypes.c_void_p(n_host.data_ptr()),
                                         ctypes.c_void_p(stream.cuda_stream))
         _lib.check(rc, "ps_raster_forward")
+        if torch.cuda.is_current_stream_capturing():
+            # CUDA-graph capture: shapes and capacity are frozen into the graph; the count still
+            # lands in pinned memory on every replay and is checked by the caller afterwards
+            if key not in _capacity_hint:
+                raise RuntimeError("run this shape once eagerly before capturing it in a CUDA graph "
+                                   "(the binning capacity must be known)")
+            return color, radii, RasterOutputState(desc, geom, binning, image, n_host, None, key)
         event = torch.cuda.Event()
         event.record(stream)
         st = RasterOutputState(desc, geom, binning, image, n_host, event, key)
