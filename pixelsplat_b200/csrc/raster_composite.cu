@@ -91,43 +91,37 @@ k_composite_fwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                     hit = (c.x + e.x >= rx0) && (c.x - e.x <= rx1) && (c.y + e.y >= ry0) && (c.y - e.y <= ry1);
                 }
                 uint32_t mask = __ballot_sync(0xffffffffu, hit);
-                // two entries per iteration: their power / exp evaluations are independent, only
+                // four entries per iteration: their power / exp evaluations are independent, only
                 // the transmittance update chains (the warp has few peers to hide latency behind:
                 // a 256x256 view is just 2048 warps on 148 SMs)
                 while (mask) {
-                    const int b0 = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const bool two = mask != 0;
-                    const int b1 = two ? __ffs(mask) - 1 : b0;
-                    mask &= mask - 1;
-                    const float2 xy0 = s.xy[jb + b0], xy1 = s.xy[jb + b1];
-                    const float4 co0 = s.co[jb + b0], co1 = s.co[jb + b1];
-                    const float4 c0 = s.rgb[jb + b0], c1 = s.rgb[jb + b1];
-                    const float dx0 = xy0.x - px, dy0 = xy0.y - py, dx1 = xy1.x - px, dy1 = xy1.y - py;
-                    const float p0 = co0.x * dx0 * dx0 + co0.z * dy0 * dy0 + co0.y * dx0 * dy0;
-                    const float p1 = co1.x * dx1 * dx1 + co1.z * dy1 * dy1 + co1.y * dx1 * dy1;
-                    const float alpha0 = fminf(0.99f, co0.w * exp2f(p0));
-                    const float alpha1 = fminf(0.99f, co1.w * exp2f(p1));
-                    {
-                        const bool contrib = !done && !(p0 > 0.0f) && !(alpha0 < kAlphaMin);
-                        const float test_T = T * (1.0f - alpha0);
-                        const bool stop = contrib && (test_T < 0.0001f);
-                        const bool blend = contrib && !stop;
-                        const float w = blend ? alpha0 * T : 0.0f;
-                        Cr += c0.x * w; Cg += c0.y * w; Cb += c0.z * w;
-                        T = blend ? test_T : T;
-                        last = blend ? round0 + jb + (uint32_t)b0 + 1u : last;
-                        done = done || stop;
+                    uint32_t jx[4];
+                    bool has[4];
+                    float pw[4], al[4];
+                    float4 col[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        has[q] = mask != 0;
+                        const int bq = has[q] ? __ffs(mask) - 1 : 0;
+                        mask &= mask - 1;
+                        jx[q] = jb + (uint32_t)bq;
+                        const float2 xy = s.xy[jx[q]];
+                        const float4 co = s.co[jx[q]];
+                        col[q] = s.rgb[jx[q]];
+                        const float dx = xy.x - px, dy = xy.y - py;
+                        pw[q] = co.x * dx * dx + co.z * dy * dy + co.y * dx * dy;
+                        al[q] = fminf(0.99f, co.w * exp2f(pw[q]));
                     }
-                    {
-                        const bool contrib = two && !done && !(p1 > 0.0f) && !(alpha1 < kAlphaMin);
-                        const float test_T = T * (1.0f - alpha1);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const bool contrib = has[q] && !done && !(pw[q] > 0.0f) && !(al[q] < kAlphaMin);
+                        const float test_T = T * (1.0f - al[q]);
                         const bool stop = contrib && (test_T < 0.0001f);
                         const bool blend = contrib && !stop;
-                        const float w = blend ? alpha1 * T : 0.0f;
-                        Cr += c1.x * w; Cg += c1.y * w; Cb += c1.z * w;
+                        const float w = blend ? al[q] * T : 0.0f;
+                        Cr += col[q].x * w; Cg += col[q].y * w; Cb += col[q].z * w;
                         T = blend ? test_T : T;
-                        last = blend ? round0 + jb + (uint32_t)b1 + 1u : last;
+                        last = blend ? round0 + jx[q] + 1u : last;
                         done = done || stop;
                     }
                 }
@@ -158,21 +152,42 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// Sum each of 16 per-lane values over the warp with 16 shuffles instead of 80: at every step a
-// lane keeps half of its values and hands the other half to its partner.  On return lane 2i
-// (and 2i+1) holds the warp total of v[i].
-__device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
+// Sum each of 32 per-lane values over the warp with 31 shuffles instead of 160: at every step a
+// lane keeps half of its values and hands the other half to its partner.  On return lane i
+// holds the warp total of v[i].
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
 #pragma unroll
-    for (int half = 8, dist = 16; half >= 1; half >>= 1, dist >>= 1) {
-        const bool up = (lane & dist) != 0;
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
 #pragma unroll
         for (int i = 0; i < half; ++i) {
             const float keep = up ? v[i + half] : v[i];
             const float send = up ? v[i] : v[i + half];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, dist);
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
         }
     }
-    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+    return v[0];
+}
+
+// Same for 4 values: lane l ends with the total of v[(l >> 3) & 3].
+__device__ __forceinline__ float transpose_reduce4(float (&v)[4], int lane) {
+    {
+        const bool up = (lane & 16) != 0;
+        const float k0 = up ? v[2] : v[0], s0 = up ? v[0] : v[2];
+        const float k1 = up ? v[3] : v[1], s1 = up ? v[1] : v[3];
+        v[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+        v[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+    }
+    {
+        const bool up = (lane & 8) != 0;
+        const float k0 = up ? v[1] : v[0], s0 = up ? v[0] : v[1];
+        v[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 8);
+    }
+    float t = v[0];
+    t += __shfl_xor_sync(0xffffffffu, t, 4);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    return t;
 }
 
 // Per-pixel backward of one list entry.  Returns whether the entry contributed;
@@ -292,36 +307,39 @@ k_composite_bwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                 hit = (c.x + e.x >= rx0) && (c.x - e.x <= rx1) && (c.y + e.y >= ry0) && (c.y - e.y <= ry1);
             }
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
-            // two list entries per iteration: their exp / gradient math is independent (only the
-            // cheap T / colour-behind recurrences chain), and one 16-wide transposed shuffle
-            // reduction serves both
+            // four list entries per iteration: their exp / gradient math is independent (only the
+            // cheap T / colour-behind recurrences chain), which gives the scheduler something to
+            // issue while shuffles are in flight (a 256x256 view is 14 warps per SM), and one
+            // 32-wide transposed shuffle reduction serves all four
             while (mask) {
-                const int b0 = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const bool two = mask != 0;
-                const int b1 = two ? __ffs(mask) - 1 : b0;
-                mask &= mask - 1;   // no-op when already 0
-                const uint32_t j0 = jb + (uint32_t)b0, j1 = jb + (uint32_t)b1;
-                float v[16], op0, op1;
-                const bool a0 = pixel_bwd((hi - 1u - j0) < last, s.xy[j0], s.co[j0], s.rgb[j0], px, py, dpr, dpg, dpb,
-                                          T_final, bg_dot, ddelx_dx, ddely_dy, st, v, op0);
-                const bool a1 = pixel_bwd(two && (hi - 1u - j1) < last, s.xy[j1], s.co[j1], s.rgb[j1], px, py, dpr,
-                                          dpg, dpb, T_final, bg_dot, ddelx_dx, ddely_dy, st, v + 8, op1);
-                const unsigned any0 = __ballot_sync(0xffffffffu, a0), any1 = __ballot_sync(0xffffffffu, a1);
-                if ((any0 | any1) == 0u) continue;
-                const float tot = transpose_reduce16(v, lane);
-                op0 = warp_sum(op0);
-                op1 = warp_sum(op1);
-                // this warp's private copy: plain read-modify-write, no other warp touches it
-                if ((lane & 1) == 0) {
-                    const int vi = lane >> 1;               // 0..15
-                    const bool second = vi >= 8;
-                    if (second ? (two && any1 != 0u) : (any0 != 0u)) s_acc[second ? j1 : j0][vi & 7] += tot;
-                } else if (lane == 1) {
-                    if (any0) s_acc[j0][8] += op0;
-                } else if (lane == 3) {
-                    if (two && any1) s_acc[j1][8] += op1;
+                uint32_t jx[4];
+                bool has[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    has[q] = mask != 0;
+                    const int bq = has[q] ? __ffs(mask) - 1 : 0;
+                    mask &= mask - 1;
+                    jx[q] = jb + (uint32_t)bq;
                 }
+                float v[32], op[4];
+                unsigned any = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool aq = pixel_bwd(has[q] && (hi - 1u - jx[q]) < last, s.xy[jx[q]], s.co[jx[q]], s.rgb[jx[q]],
+                                              px, py, dpr, dpg, dpb, T_final, bg_dot, ddelx_dx, ddely_dy, st,
+                                              v + 8 * q, op[q]);
+                    any |= __ballot_sync(0xffffffffu, aq) ? (1u << q) : 0u;
+                }
+                if (any == 0u) continue;
+                const float tot = transpose_reduce32(v, lane);      // lane 8q + k: value k of entry q
+                const float opt = transpose_reduce4(op, lane);      // lanes 8q ..: opacity of entry q
+                // this warp's private copy: plain read-modify-write, no other warp touches it
+                const int q = lane >> 3, k = lane & 7;
+                const uint32_t jq = q == 0 ? jx[0] : q == 1 ? jx[1] : q == 2 ? jx[2] : jx[3];
+                const bool live_q = (any >> q) & 1u;
+                if (live_q) s_acc[jq][k] += tot;
+                __syncwarp();
+                if (live_q && k == 0) s_acc[jq][8] += opt;
                 __syncwarp();
             }
         }
