@@ -234,7 +234,7 @@ k_tile_sort(const uint32_t *__restrict__ tile_start, const uint32_t *__restrict_
 // compare-exchange steps, and it is oblivious to ties.  One CTA per (view, tile); segments
 // longer than `cap` (a power of two, chosen by the host from the previous call's longest
 // segment) are left to the radix kernel.
-constexpr int kBitonicThreads = 512;
+constexpr int kBitonicThreads = 1024;
 
 __global__ void __launch_bounds__(kBitonicThreads)
 k_tile_sort_bitonic(const uint32_t *__restrict__ tile_start, const uint32_t *__restrict__ tile_count,

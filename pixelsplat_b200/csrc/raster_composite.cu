@@ -45,6 +45,14 @@ struct StageBuf {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
+// 2^x with the hardware approximation only (MUFU.EX2, flush-to-zero); exp2f() adds denormal
+// range handling that the compositor does not need (alpha below 1/255 is discarded anyway).
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ void stage_entry(StageBuf &s, int slot, const Geom &geo, size_t base, uint32_t g) {
     const float4 co = geo.conic_opacity[base + g];
     s.xy[slot] = geo.xy[base + g];
@@ -110,7 +118,7 @@ k_composite_fwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                         col[q] = s.rgb[jx[q]];
                         const float dx = xy.x - px, dy = xy.y - py;
                         pw[q] = co.x * dx * dx + co.z * dy * dy + co.y * dx * dy;
-                        al[q] = fminf(0.99f, co.w * exp2f(pw[q]));
+                        al[q] = fminf(0.99f, co.w * fast_exp2(pw[q]));
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -205,35 +213,34 @@ __device__ __forceinline__ bool pixel_bwd(bool in_range, const float2 exy, const
                                           float *g, float &op) {
     const float dx = exy.x - px, dy = exy.y - py;
     const float p2 = eco.x * dx * dx + eco.z * dy * dy + eco.y * dx * dy;   // power * log2(e)
-    const float G = exp2f(p2);
+    const float G = fast_exp2(p2);
     const float alpha = fminf(0.99f, eco.w * G);
     const bool active = in_range && !(p2 > 0.0f) && !(alpha < kAlphaMin);
+    // An entry the pixel skips behaves exactly like one with alpha = 0 and G = 0: T is unchanged,
+    // the colour-behind recurrence folds the previous entry and then carries a zero-weight one,
+    // and every gradient term vanishes -- so no per-field predication is needed.
     const float a = active ? alpha : 0.0f;
-    const float rcp = __fdividef(1.0f, 1.0f - a);                              // 1 when inactive
+    const float Gs = active ? G : 0.0f;             // also keeps an overflowed exp2 out of 0 * inf
+    const float rcp = __fdividef(1.0f, 1.0f - a);
     st.T = st.T * rcp;
-    const float dchannel_dcolor = a * st.T;
-    const float la = st.last_alpha, one_m = 1.0f - la;
-    const float nr = la * st.lc_r + one_m * st.acc_r, ng = la * st.lc_g + one_m * st.acc_g,
-                nb = la * st.lc_b + one_m * st.acc_b;
-    st.acc_r = active ? nr : st.acc_r; st.acc_g = active ? ng : st.acc_g; st.acc_b = active ? nb : st.acc_b;
-    st.lc_r = active ? ergb.x : st.lc_r; st.lc_g = active ? ergb.y : st.lc_g; st.lc_b = active ? ergb.z : st.lc_b;
-    st.last_alpha = active ? alpha : la;
-    float dL_dalpha = (ergb.x - nr) * dpr + (ergb.y - ng) * dpg + (ergb.z - nb) * dpb;
+    const float la = st.last_alpha;
+    st.acc_r = st.acc_r + la * (st.lc_r - st.acc_r);      // = la * lc + (1 - la) * acc
+    st.acc_g = st.acc_g + la * (st.lc_g - st.acc_g);
+    st.acc_b = st.acc_b + la * (st.lc_b - st.acc_b);
+    st.lc_r = ergb.x; st.lc_g = ergb.y; st.lc_b = ergb.z;
+    st.last_alpha = a;
+    const float w_color = a * st.T;
+    g[5] = w_color * dpr; g[6] = w_color * dpg; g[7] = w_color * dpb;
+    float dL_dalpha = (ergb.x - st.acc_r) * dpr + (ergb.y - st.acc_g) * dpg + (ergb.z - st.acc_b) * dpb;
     dL_dalpha = dL_dalpha * st.T - T_final * rcp * bg_dot;
-    dL_dalpha = active ? dL_dalpha : 0.0f;
-    g[5] = dchannel_dcolor * dpr; g[6] = dchannel_dcolor * dpg; g[7] = dchannel_dcolor * dpb;
-    const float dL_dG = eco.w * dL_dalpha;
-    const float Gs = active ? G : 0.0f;   // exp2 of a non-PSD conic may overflow: keep 0 * inf out
-    const float gdx = Gs * dx, gdy = Gs * dy;
+    const float wG = eco.w * dL_dalpha * Gs;        // dL/dG * G
+    const float sx = wG * dx, sy = wG * dy;
     // dG/d(delta) = -G (A dx + B dy) with A = -2 qa / log2e, B = -qb / log2e
-    const float dG_ddelx = kLn2 * (2.0f * eco.x * gdx + eco.y * gdy);
-    const float dG_ddely = kLn2 * (2.0f * eco.z * gdy + eco.y * gdx);
-    g[0] = dL_dG * dG_ddelx * ddelx_dx;
-    g[1] = dL_dG * dG_ddely * ddely_dy;
-    const float h = -0.5f * dL_dG;
-    g[2] = h * gdx * dx;
-    g[3] = h * gdx * dy;
-    g[4] = h * gdy * dy;
+    g[0] = (kLn2 * ddelx_dx) * (2.0f * eco.x * sx + eco.y * sy);
+    g[1] = (kLn2 * ddely_dy) * (2.0f * eco.z * sy + eco.y * sx);
+    g[2] = -0.5f * sx * dx;
+    g[3] = -0.5f * sx * dy;
+    g[4] = -0.5f * sy * dy;
     op = Gs * dL_dalpha;
     return active;
 }

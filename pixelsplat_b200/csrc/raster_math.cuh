@@ -132,7 +132,7 @@ __device__ __forceinline__ void sh_for_each(int deg, float x, float y, float z, 
 __device__ __forceinline__ void stage_sh_rows(const float *__restrict__ src, float *dst, int rows, int sh_n,
                                               int row_stride, int lane) {
     const int total = rows * sh_n;
-    const bool vec_ok = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
     if (row_stride == sh_n) {
         // odd row length (M = 1, 9, 25): rows are already conflict-free, the copy is linear
         const int nvec = vec_ok ? total >> 2 : 0;
@@ -156,7 +156,7 @@ __device__ __forceinline__ void unstage_sh_rows(const float *src, float *__restr
                                                 int row_stride, int lane) {
     const int total = rows * sh_n;
     if (row_stride == sh_n) {
-        const bool vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
         const int nvec = vec_ok ? total >> 2 : 0;
         for (int i = lane; i < nvec; i += 32)
             reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(src)[i];

@@ -18,7 +18,8 @@ k_preprocess(Dims d, Inputs in, Geom geo, int use_smem_hist, int row_stride) {
     extern __shared__ uint32_t s_dyn[];
     uint32_t *s_hist = s_dyn;                                    // [V * tiles] when use_smem_hist
     const int hist_n = d.V * d.tiles;
-    float *s_sh = reinterpret_cast<float *>(s_dyn + (use_smem_hist ? hist_n : 0));   // [warps][32][row_stride]
+    // [warps][32][row_stride], placed after the histogram rounded up to 16 bytes (float4 staging)
+    float *s_sh = reinterpret_cast<float *>(s_dyn + (use_smem_hist ? ((hist_n + 3) & ~3) : 0));
     const int scene = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g0 = blockIdx.x * kPreThreads + warp * 32;
@@ -156,7 +157,7 @@ int launch_preprocess(const Dims &d, const Inputs &in, const Geom &g, cudaStream
     const int use_smem = hist_bytes <= 32 * 1024;
     const int row_stride = d.M > 0 ? ((3 * d.M) | 1) : 1;
     const size_t sh_bytes = d.M > 0 ? sizeof(float) * kPreThreads * row_stride : 0;
-    const size_t smem = (use_smem ? hist_bytes : 0) + sh_bytes;
+    const size_t smem = (use_smem ? ((hist_bytes + 15) & ~(size_t)15) : 0) + sh_bytes;
     static bool attr = false;
     if (!attr) {
         PS_CUDA_CHECK(cudaFuncSetAttribute(k_preprocess, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
