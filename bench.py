@@ -222,6 +222,7 @@ def main():
     ap.add_argument("--views", type=int, default=1, help="target views per step (one scene)")
     ap.add_argument("--pool", type=int, default=4, help="distinct scenes cycled (> L2 in total)")
     ap.add_argument("--streams", type=int, default=4, help="extra leg: steps issued over N streams")
+    ap.add_argument("--batched-views", type=int, default=4, help="extra leg: V target views per call")
     ap.add_argument("--no-graph", action="store_true", help="issue every step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -332,6 +333,36 @@ def main():
         concurrent = {"streams": args.streams, "value": world * K * V / dtc, "unit": UNIT,
                       "how": "wall clock, steps round-robin over CUDA streams, same pool of scenes"}
 
+    # ---------------- extra: the training shape -- 4 target views of one scene share its Gaussians
+    # in ONE call (V cameras per Gaussian set; the reference repeats every Gaussian tensor per
+    # view, decoder_splatting_cuda.py:53-56).  Reported separately; configs[1] is 1 view per step.
+    batched = None
+    if args.batched_views > 1 and not args.no_graph:
+        Vb = args.batched_views
+        hb = scene_host_tensors(make_scene(1000 * rank + 500, Vb), pin=False)
+        db = {k: v.to(dev) for k, v in hb.items()}
+        for k in GAUSS_KEYS:
+            db[k].requires_grad_(True)
+        d_img_b = torch.randn((1, Vb, 3, *IMAGE), generator=g).to(dev)
+        rasterizer.set_capacity_check("sync")
+        render_step(db, d_img_b, Vb)
+        rasterizer.set_capacity_check("deferred")
+        gb, _, states_b = capture_step(db, d_img_b, Vb)
+        for _ in range(W_):
+            gb.replay()
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nb = max(K // Vb, 10)
+        b0.record()
+        for _ in range(nb):
+            gb.replay()
+        b1.record()
+        barrier()
+        for st_ in states_b:
+            st_.verify()
+        batched = {"views_per_call": Vb, "value": world * nb * Vb / (b0.elapsed_time(b1) * 1e-3), "unit": UNIT,
+                   "how": "one scene, V target cameras sharing its Gaussians in a single forward+backward"}
+
     # ---------------- e2e: host buffers, H2D + fwd + bwd + D2H per step, prefetch on a side stream
     e2e = None
     if not args.no_e2e:
@@ -439,7 +470,7 @@ def main():
                        "capacity_check": "deferred (verified at backward)",
                        "launch": "eager python" if args.no_graph else "one CUDA graph per scene (fwd+bwd), replayed"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "stage_ms": stage_ms, "workload_stats": stats, "throughput_concurrent_streams": concurrent,
+            "roofline": roofline, "cpu_baseline": cpu, "stage_ms": stage_ms, "workload_stats": stats, "throughput_concurrent_streams": concurrent, "throughput_batched_views": batched,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -108,7 +108,10 @@ typedef struct ps_raster_layout {
     size_t tile_count;    /* u32  [S*V*tiles]                                                  */
     size_t tile_start;    /* u32  [S*V*tiles] exclusive scan, global instance offsets          */
     size_t tile_cursor;   /* u32  scratch                                                      */
-    size_t n_instances;   /* i64  [2] total instances needed (may exceed capacity), longest segment */
+    size_t n_instances;   /* i64  [4] instances needed (may exceed capacity), longest segment,
+                                     #visible (view,Gaussian) pairs, #Gaussians visible in any view */
+    size_t vis_pairs;     /* u32  [S*V*P] compact list of on-screen (view,Gaussian) flat indices  */
+    size_t vis_any;       /* u32  [S*P]   compact list of (scene,Gaussian) visible in >= 1 view    */
     /* binning */
     size_t keys;          /* u64  [capacity]  per tile sorted (float_bits(depth)<<32 | gaussian) */
     size_t keys_alt;      /* u64  [capacity]  scratch                                          */

@@ -22,7 +22,9 @@ struct Geom {
     uint32_t *tile_count;
     uint32_t *tile_start;
     uint32_t *tile_cursor;
-    long long *n_instances;
+    long long *n_instances;   // [0] instances, [1] longest segment, [2] #vis_pairs, [3] #vis_any
+    uint32_t *vis_pairs;      // compact list of (view, Gaussian) flat indices that are on screen
+    uint32_t *vis_any;        // compact list of (scene, Gaussian) flat indices visible in >= 1 view
 };
 
 struct Dims {
@@ -82,5 +84,6 @@ int launch_composite_backward(const Dims &d, const Inputs &in, const Geom &g,
                               cudaStream_t st);
 int launch_preprocess_backward(const Dims &d, const Inputs &in, const Geom &g, const ViewGrads &vg,
                                const ps_raster_grads &out, cudaStream_t st);
+int launch_gradient_fill(const Dims &d, const ps_raster_grads &out, cudaStream_t st);
 
 }  // namespace ps

@@ -32,6 +32,19 @@ void mark(int id, cudaStream_t st) {
     cudaEventRecord(g_events[id], st);
 }
 
+// Side stream for work that is independent of the critical path (gradient zero-fill overlapping
+// the composite backward).  Fork/join with events, which also captures cleanly into CUDA graphs.
+static cudaStream_t g_side = nullptr;
+static cudaEvent_t g_fork = nullptr, g_join = nullptr;
+
+static int side_ready() {
+    if (g_side) return PS_OK;
+    PS_CUDA_CHECK(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
+    PS_CUDA_CHECK(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
+    PS_CUDA_CHECK(cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming));
+    return PS_OK;
+}
+
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Layout {
@@ -63,6 +76,10 @@ static int validate(const ps_raster_desc *d) {
     const long long gx = (d->width + kTile - 1) / kTile, gy = (d->height + kTile - 1) / kTile;
     if (gx > 65535 || gy > 65535) { set_error("image too large for 16-bit tile rectangles"); return PS_ERR_UNSUPPORTED; }
     const long long segs = (long long)d->n_scenes * d->views_per_scene * gx * gy;
+    if ((long long)d->n_scenes * d->views_per_scene * d->n_gaussians > 0xffffffffll) {
+        set_error("scenes * views * gaussians must fit 32 bits");
+        return PS_ERR_UNSUPPORTED;
+    }
     if (segs > 0x7fffffffll || (long long)d->n_scenes * d->views_per_scene > 65535) {
         set_error("too many (view, tile) segments: %lld", segs);
         return PS_ERR_UNSUPPORTED;
@@ -99,7 +116,9 @@ static Layout make_layout(const ps_raster_desc *d) {
     L.off.tile_count = take(vt * 4);
     L.off.tile_start = take(vt * 4);
     L.off.tile_cursor = take(vt * 4);
-    L.off.n_instances = take(16);   // [0] total instances, [1] longest segment
+    L.off.n_instances = take(32);   // [0] instances, [1] longest segment, [2] #visible pairs, [3] #visible Gaussians
+    L.off.vis_pairs = take(vp * 4);
+    L.off.vis_any = take((size_t)m.S * m.P * 4);
     L.sizes.geom_bytes = o;
     o = 0;
     L.off.keys = take((size_t)m.capacity * 8);
@@ -128,6 +147,8 @@ static Geom make_geom(const Layout &L, void *geom) {
     g.tile_start = reinterpret_cast<uint32_t *>(b + L.off.tile_start);
     g.tile_cursor = reinterpret_cast<uint32_t *>(b + L.off.tile_cursor);
     g.n_instances = reinterpret_cast<long long *>(b + L.off.n_instances);
+    g.vis_pairs = reinterpret_cast<uint32_t *>(b + L.off.vis_pairs);
+    g.vis_any = reinterpret_cast<uint32_t *>(b + L.off.vis_any);
     return g;
 }
 
@@ -269,10 +290,17 @@ PS_API int ps_raster_backward(const ps_raster_desc *desc, const ps_raster_inputs
     vg.d_conic = reinterpret_cast<float4 *>(sb + align_up(vp * 8));
     vg.d_color = reinterpret_cast<float4 *>(sb + align_up(vp * 8) + align_up(vp * 16));
     mark(kMarkBwdStart, st);
+    if ((rc = side_ready())) return rc;
+    // fork: zero the output gradients on the side stream while the composite backward runs
+    PS_CUDA_CHECK(cudaEventRecord(g_fork, st));
+    PS_CUDA_CHECK(cudaStreamWaitEvent(g_side, g_fork, 0));
+    if ((rc = launch_gradient_fill(d, *grads, g_side))) return rc;
+    PS_CUDA_CHECK(cudaEventRecord(g_join, g_side));
     PS_CUDA_CHECK(cudaMemsetAsync(scratch, 0, L.sizes.backward_bytes, st));
     mark(kMarkBwdZero, st);
     if ((rc = launch_composite_backward(d, I, g, keys, final_T, n_contrib, d_color, vg, st))) return rc;
     mark(kMarkCompositeBwd, st);
+    PS_CUDA_CHECK(cudaStreamWaitEvent(st, g_join, 0));   // join
     if ((rc = launch_preprocess_backward(d, I, g, vg, *grads, st))) return rc;
     mark(kMarkPreprocessBwd, st);
     return PS_OK;

@@ -13,17 +13,30 @@ namespace ps {
 
 constexpr int kPreThreads = 128;
 
-__global__ void __launch_bounds__(kPreThreads, 4)
-k_preprocess(Dims d, Inputs in, Geom geo, int use_smem_hist, int row_stride) {
-    extern __shared__ uint32_t s_dyn[];
-    uint32_t *s_hist = s_dyn;                                    // [V * tiles] when use_smem_hist
+// Appends the flat indices of the lanes with `flag` to a compact list: one global atomic per warp.
+__device__ __forceinline__ void warp_append(bool flag, uint32_t value, uint32_t *list, long long *counter, int lane) {
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (m == 0u) return;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader)
+        base = atomicAdd(reinterpret_cast<unsigned long long *>(counter), (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (flag) list[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
+// Geometry for every (scene, Gaussian) x view.  Only a third of the Gaussians of a pixelSplat
+// scene land on a given target view, and they are interleaved with the off-screen ones (three
+// depth samples per context pixel), so everything that only on-screen Gaussians need -- the
+// 300-byte SH row and its evaluation -- is deferred to k_sh_color, which runs densely over the
+// compact list built here.
+__global__ void __launch_bounds__(kPreThreads)
+k_preprocess(Dims d, Inputs in, Geom geo, int use_smem_hist) {
+    extern __shared__ uint32_t s_hist[];                         // [V * tiles] when use_smem_hist
     const int hist_n = d.V * d.tiles;
-    // [warps][32][row_stride], placed after the histogram rounded up to 16 bytes (float4 staging)
-    float *s_sh = reinterpret_cast<float *>(s_dyn + (use_smem_hist ? ((hist_n + 3) & ~3) : 0));
     const int scene = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g0 = blockIdx.x * kPreThreads + warp * 32;
-    const int g = g0 + lane;
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kPreThreads + threadIdx.x;
     const bool live = g < d.P;
     if (use_smem_hist) {
         for (int i = threadIdx.x; i < hist_n; i += kPreThreads) s_hist[i] = 0;
@@ -36,9 +49,7 @@ k_preprocess(Dims d, Inputs in, Geom geo, int use_smem_hist, int row_stride) {
         opacity = in.opac[sg];
     }
     const float *covp = in.cov + sg * (d.cov_layout == PS_COV_TRIU6 ? 6 : 9);
-    const int sh_n = 3 * d.M;
-    float *row = s_sh + ((size_t)warp * 32 + lane) * row_stride;
-    bool staged = false;
+    bool any_vis = false;
 
     for (int v = 0; v < d.V; ++v) {
         const int vid = scene * d.V + v;
@@ -50,10 +61,7 @@ k_preprocess(Dims d, Inputs in, Geom geo, int use_smem_hist, int row_stride) {
         const float py = in.scale ? my0 * sc : my0;
         const float pz = in.scale ? mz0 * sc : mz0;
         bool vis = live;
-        float vz = 0.0f, pixx = 0.0f, pixy = 0.0f, det_inv = 0.0f;
-        int r = 0, minx = 0, miny = 0, maxx = 0, maxy = 0;
-        Cov2D cv;
-        cv.a = cv.b = cv.c = 0.0f;
+        float vz = 0.0f;
         if (vis) {
             geo.radii[vg] = 0;
             vz = vm[2] * px + vm[6] * py + vm[10] * pz + vm[14];
@@ -70,77 +78,50 @@ k_preprocess(Dims d, Inputs in, Geom geo, int use_smem_hist, int row_stride) {
             const float focal_y = (float)d.H / (2.0f * tanfovy);
             float s6[6];
             load_cov6(covp, d.cov_layout, in.scale ? sc * sc : 1.0f, s6);
+            Cov2D cv;
             compute_cov2d(px, py, pz, s6, vm, focal_x, focal_y, tanfovx, tanfovy, cv);
             const float det = cv.a * cv.c - cv.b * cv.b;
             vis = !(det == 0.0f);
             if (vis) {
-                det_inv = 1.0f / det;
+                const float det_inv = 1.0f / det;
                 const float mid = 0.5f * (cv.a + cv.c);
                 const float sq = sqrtf(fmaxf(0.1f, mid * mid - det));
                 const float lambda1 = mid + sq, lambda2 = mid - sq;
                 const float my_radius = ceilf(3.0f * sqrtf(fmaxf(lambda1, lambda2)));
-                pixx = ((projx + 1.0f) * (float)d.W - 1.0f) * 0.5f;
-                pixy = ((projy + 1.0f) * (float)d.H - 1.0f) * 0.5f;
-                r = (int)my_radius;
+                const float pixx = ((projx + 1.0f) * (float)d.W - 1.0f) * 0.5f;
+                const float pixy = ((projy + 1.0f) * (float)d.H - 1.0f) * 0.5f;
+                const int r = (int)my_radius;
                 const float rf = (float)r;
-                minx = min(d.gx, max(0, (int)((pixx - rf) / (float)kTile)));
-                miny = min(d.gy, max(0, (int)((pixy - rf) / (float)kTile)));
-                maxx = min(d.gx, max(0, (int)((pixx + rf + (float)(kTile - 1)) / (float)kTile)));
-                maxy = min(d.gy, max(0, (int)((pixy + rf + (float)(kTile - 1)) / (float)kTile)));
+                const int minx = min(d.gx, max(0, (int)((pixx - rf) / (float)kTile)));
+                const int miny = min(d.gy, max(0, (int)((pixy - rf) / (float)kTile)));
+                const int maxx = min(d.gx, max(0, (int)((pixx + rf + (float)(kTile - 1)) / (float)kTile)));
+                const int maxy = min(d.gy, max(0, (int)((pixy + rf + (float)(kTile - 1)) / (float)kTile)));
                 vis = (maxx - minx) * (maxy - miny) != 0;
-            }
-        }
-        // the warp's SH rows are brought in once, the first time any of its Gaussians is on screen
-        if (d.M > 0 && !staged && __any_sync(0xffffffffu, vis)) {
-            const int rows = min(32, d.P - g0);
-            stage_sh_rows(in.sh + ((size_t)scene * d.P + g0) * (size_t)sh_n, s_sh + (size_t)warp * 32 * row_stride,
-                          rows, sh_n, row_stride, lane);
-            __syncwarp();
-            staged = true;
-        }
-        if (!vis) continue;
-
-        float rgb[3];
-        uint8_t clamp_bits = 0;
-        if (d.M > 0) {
-            const float cx = in.campos[3 * vid], cy = in.campos[3 * vid + 1], cz = in.campos[3 * vid + 2];
-            const float ddx = px - cx, ddy = py - cy, ddz = pz - cz;
-            const float len = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
-            const float x = ddx / len, y = ddy / len, z = ddz / len;
-            float acc[3] = {0.0f, 0.0f, 0.0f};
-            const int M = d.M, layout = d.sh_layout;
-            sh_for_each(d.deg, x, y, z, [&](int k, float Y, float, float, float) {
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    const float c = row[sh_index(layout, M, k, ch)];
-                    acc[ch] = k == 0 ? Y * c : acc[ch] + Y * c;
+                if (vis) {
+                    geo.depth[vg] = vz;
+                    geo.radii[vg] = r;
+                    geo.xy[vg] = make_float2(pixx, pixy);
+                    geo.conic_opacity[vg] = make_float4(cv.c * det_inv, -cv.b * det_inv, cv.a * det_inv, opacity);
+                    geo.rect[vg] = make_ushort4((unsigned short)minx, (unsigned short)miny,
+                                                (unsigned short)maxx, (unsigned short)maxy);
+                    if (d.M == 0) {
+                        const float *__restrict__ col = in.sh + sg * 3;
+                        geo.rgb[vg] = make_float4(col[0], col[1], col[2], 0.0f);
+                        geo.clamped[vg] = 0;
+                    }
+                    for (int ty = miny; ty < maxy; ++ty)
+                        for (int tx = minx; tx < maxx; ++tx) {
+                            const int t = ty * d.gx + tx;
+                            if (use_smem_hist) atomicAdd(&s_hist[v * d.tiles + t], 1u);
+                            else atomicAdd(&geo.tile_count[(size_t)vid * d.tiles + t], 1u);
+                        }
                 }
-            });
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                const float a = acc[ch] + 0.5f;
-                if (a < 0.0f) clamp_bits |= (uint8_t)(1u << ch);
-                rgb[ch] = fmaxf(a, 0.0f);
             }
-        } else {
-            const float *__restrict__ col = in.sh + sg * 3;
-            rgb[0] = col[0]; rgb[1] = col[1]; rgb[2] = col[2];
         }
-        geo.depth[vg] = vz;
-        geo.radii[vg] = r;
-        geo.xy[vg] = make_float2(pixx, pixy);
-        geo.conic_opacity[vg] = make_float4(cv.c * det_inv, -cv.b * det_inv, cv.a * det_inv, opacity);
-        geo.rgb[vg] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
-        geo.rect[vg] = make_ushort4((unsigned short)minx, (unsigned short)miny,
-                                    (unsigned short)maxx, (unsigned short)maxy);
-        geo.clamped[vg] = clamp_bits;
-        for (int ty = miny; ty < maxy; ++ty)
-            for (int tx = minx; tx < maxx; ++tx) {
-                const int t = ty * d.gx + tx;
-                if (use_smem_hist) atomicAdd(&s_hist[v * d.tiles + t], 1u);
-                else atomicAdd(&geo.tile_count[(size_t)vid * d.tiles + t], 1u);
-            }
+        any_vis |= vis;
+        warp_append(vis, (uint32_t)vg, geo.vis_pairs, geo.n_instances + 2, lane);
     }
+    warp_append(any_vis, (uint32_t)sg, geo.vis_any, geo.n_instances + 3, lane);
     if (use_smem_hist) {
         __syncthreads();
         uint32_t *dst = geo.tile_count + (size_t)scene * d.V * d.tiles;
@@ -151,21 +132,86 @@ k_preprocess(Dims d, Inputs in, Geom geo, int use_smem_hist, int row_stride) {
     }
 }
 
+// SH -> RGB for the on-screen (view, Gaussian) pairs only, one thread per pair (dense warps).
+// The warp first copies its 32 (scattered) 3M-float rows into shared memory with coalesced
+// row-wise loads, then every lane evaluates its own row.
+constexpr int kShThreads = 128;
+
+__global__ void __launch_bounds__(kShThreads)
+k_sh_color(Dims d, Inputs in, Geom geo, int row_stride) {
+    extern __shared__ float s_rows[];                            // [warps][32][row_stride]
+    const long long n = geo.n_instances[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long i0 = ((long long)blockIdx.x * kShThreads) + warp * 32;
+    if (i0 >= n) return;
+    const long long i = i0 + lane;
+    const bool live = i < n;
+    const uint32_t vg = live ? geo.vis_pairs[i] : 0u;
+    const uint32_t vid = vg / (uint32_t)d.P, g = vg - vid * (uint32_t)d.P;
+    const uint32_t scene = vid / (uint32_t)d.V;
+    const size_t sg = (size_t)scene * d.P + g;
+    const int sh_n = 3 * d.M;
+    float *wrows = s_rows + (size_t)warp * 32 * row_stride;
+    // cooperative row loads: lane l fetches floats l, l+32, ... of every row
+    for (int r = 0; r < 32; ++r) {
+        const size_t rsg = __shfl_sync(0xffffffffu, (unsigned long long)sg, r);
+        if (i0 + r < n) {
+            const float *__restrict__ src = in.sh + rsg * (size_t)sh_n;
+            for (int c = lane; c < sh_n; c += 32) wrows[r * row_stride + c] = __ldg(src + c);
+        }
+    }
+    __syncwarp();
+    if (!live) return;
+    const float sc = in.scale ? in.scale[vid] : 1.0f;
+    const float m0 = in.means[3 * sg + 0], m1 = in.means[3 * sg + 1], m2 = in.means[3 * sg + 2];
+    const float px = in.scale ? m0 * sc : m0, py = in.scale ? m1 * sc : m1, pz = in.scale ? m2 * sc : m2;
+    const float cx = in.campos[3 * vid], cy = in.campos[3 * vid + 1], cz = in.campos[3 * vid + 2];
+    const float ddx = px - cx, ddy = py - cy, ddz = pz - cz;
+    const float len = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
+    const float x = ddx / len, y = ddy / len, z = ddz / len;
+    const float *row = wrows + lane * row_stride;
+    float acc[3] = {0.0f, 0.0f, 0.0f};
+    const int M = d.M, layout = d.sh_layout;
+    sh_for_each(d.deg, x, y, z, [&](int k, float Y, float, float, float) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float c = row[sh_index(layout, M, k, ch)];
+            acc[ch] = k == 0 ? Y * c : acc[ch] + Y * c;
+        }
+    });
+    float rgb[3];
+    uint8_t clamp_bits = 0;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float a = acc[ch] + 0.5f;
+        if (a < 0.0f) clamp_bits |= (uint8_t)(1u << ch);
+        rgb[ch] = fmaxf(a, 0.0f);
+    }
+    geo.rgb[vg] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+    geo.clamped[vg] = clamp_bits;
+}
+
 int launch_preprocess(const Dims &d, const Inputs &in, const Geom &g, cudaStream_t st) {
     PS_CUDA_CHECK(cudaMemsetAsync(g.tile_count, 0, sizeof(uint32_t) * (size_t)d.S * d.V * d.tiles, st));
+    PS_CUDA_CHECK(cudaMemsetAsync(g.n_instances, 0, 4 * sizeof(long long), st));
     const size_t hist_bytes = sizeof(uint32_t) * (size_t)d.V * d.tiles;
     const int use_smem = hist_bytes <= 32 * 1024;
-    const int row_stride = d.M > 0 ? ((3 * d.M) | 1) : 1;
-    const size_t sh_bytes = d.M > 0 ? sizeof(float) * kPreThreads * row_stride : 0;
-    const size_t smem = (use_smem ? ((hist_bytes + 15) & ~(size_t)15) : 0) + sh_bytes;
-    static bool attr = false;
-    if (!attr) {
-        PS_CUDA_CHECK(cudaFuncSetAttribute(k_preprocess, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr = true;
-    }
     dim3 grid((d.P + kPreThreads - 1) / kPreThreads, d.S);
-    k_preprocess<<<grid, kPreThreads, smem, st>>>(d, in, g, use_smem, row_stride);
+    k_preprocess<<<grid, kPreThreads, use_smem ? hist_bytes : 0, st>>>(d, in, g, use_smem);
     PS_LAUNCH_CHECK("k_preprocess");
+    if (d.M > 0) {
+        // the pair count lives on the device: launch for the worst case, surplus warps exit at once
+        const int row_stride = (3 * d.M) | 1;
+        const size_t smem = sizeof(float) * kShThreads * row_stride;
+        static bool attr = false;
+        if (!attr) {
+            PS_CUDA_CHECK(cudaFuncSetAttribute(k_sh_color, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            attr = true;
+        }
+        const long long pairs = (long long)d.S * d.V * d.P;
+        k_sh_color<<<(unsigned)((pairs + kShThreads - 1) / kShThreads), kShThreads, smem, st>>>(d, in, g, row_stride);
+        PS_LAUNCH_CHECK("k_sh_color");
+    }
     return PS_OK;
 }
 

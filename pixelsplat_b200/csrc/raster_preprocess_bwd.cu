@@ -13,32 +13,47 @@
 namespace ps {
 
 constexpr int kPreBwdThreads = 128;
-constexpr int kPreBwdWarps = kPreBwdThreads / 32;
 
-// dL/dSH is staged per warp in shared memory ([32 Gaussians][3M floats], row stride padded to an
-// odd word count so the per-lane rows are bank-conflict free) and written out as one contiguous
-// 32*3M-float run with 16-byte stores.  A thread-per-Gaussian direct write would issue 3M
-// 4-byte stores at a 12M-byte stride: 8x the L2 write transactions, which was the limiter
-// (202 us -> see profiles/).
+// One thread per Gaussian that is on screen in at least one view (the compact list built by the
+// forward pass), so warps are dense; Gaussians that are not listed receive zero gradients from
+// launch_gradient_fill (plain memsets, issued on a side stream so that they overlap the
+// compute-bound composite backward).  SH rows are staged per warp in shared memory: coefficients
+// come in with coalesced row-wise loads, dL/dSH goes out the same way.
 __global__ void __launch_bounds__(kPreBwdThreads, 4)
 k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out, int row_stride) {
-    extern __shared__ float s_dsh[];   // [warps][32][row_stride]
-    const int scene = blockIdx.y;
+    extern __shared__ float s_dsh[];   // [warps][32][row_stride] coefficients (V == 1: reused for the gradient)
+    if (*geo.n_instances > d.capacity) return;
+    const long long n = geo.n_instances[3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g0 = blockIdx.x * kPreBwdThreads + warp * 32;   // first Gaussian of this warp
-    const int g = g0 + lane;
-    const bool live = g < d.P;
-    const size_t sg = (size_t)scene * d.P + (live ? g : 0);
-    const bool truncated = *geo.n_instances > d.capacity;
+    const long long i0 = ((long long)blockIdx.x * kPreBwdThreads) + warp * 32;
+    if (i0 >= n) return;
+    const long long li = i0 + lane;
+    const bool live = li < n;
+    const uint32_t sgi = live ? geo.vis_any[li] : 0u;
+    const uint32_t scene = sgi / (uint32_t)d.P, g = sgi - scene * (uint32_t)d.P;
+    const size_t sg = sgi;
     const int cov_n = d.cov_layout == PS_COV_TRIU6 ? 6 : 9;
     const int sh_n = d.M > 0 ? 3 * d.M : 3;
-    float *row = s_dsh + ((size_t)warp * 32 + lane) * row_stride;
     const int M = d.M, layout = d.sh_layout;
+    float *wrows = s_dsh + (size_t)warp * 32 * row_stride;
+    float *row = wrows + lane * row_stride;
+    const bool in_place = M > 0 && d.V == 1;     // read each coefficient, then overwrite its slot with the gradient
+    float *grow = in_place ? row : row + (size_t)kPreBwdThreads * row_stride;   // separate gradient rows when V > 1
+
+    if (M > 0) {
+        for (int r = 0; r < 32; ++r) {
+            const size_t rsg = __shfl_sync(0xffffffffu, (unsigned long long)sg, r);
+            if (i0 + r < n) {
+                const float *__restrict__ src = in.sh + rsg * (size_t)sh_n;
+                for (int c = lane; c < sh_n; c += 32) wrows[r * row_stride + c] = __ldg(src + c);
+            }
+        }
+        __syncwarp();
+    }
 
     float mx0 = 0.0f, my0 = 0.0f, mz0 = 0.0f;
     if (live) { mx0 = in.means[3 * sg + 0]; my0 = in.means[3 * sg + 1]; mz0 = in.means[3 * sg + 2]; }
     const float *covp = in.cov + sg * cov_n;
-    const float *__restrict__ sh = in.sh + sg * (size_t)sh_n;
 
     float dmx = 0.0f, dmy = 0.0f, dmz = 0.0f, dop = 0.0f;
     float dcov[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
@@ -46,22 +61,13 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
     bool sh_written = false;
 
     for (int v = 0; v < d.V; ++v) {
-        const int vid = scene * d.V + v;
-        const size_t vg = (size_t)vid * d.P + (live ? g : 0);
-        const bool vis = live && !truncated && geo.radii[vg] > 0;
-        if (live && out.d_means2d) {
+        const int vid = (int)scene * d.V + v;
+        const size_t vg = (size_t)vid * d.P + g;
+        const bool vis = live && geo.radii[vg] > 0;
+        if (live && out.d_means2d && vis) {
             float *m2 = out.d_means2d + 3 * vg;
-            const float2 t = vis ? vgr.d_mean2d[vg] : make_float2(0.0f, 0.0f);
-            m2[0] = t.x; m2[1] = t.y; m2[2] = 0.0f;
-        }
-        // single-view calls: the warp's SH coefficients are staged (coalesced) into the same
-        // shared rows that will receive the gradient; each coefficient is read just before its
-        // slot is overwritten
-        const bool staged_in_place = M > 0 && d.V == 1;
-        if (staged_in_place && __any_sync(0xffffffffu, vis)) {
-            stage_sh_rows(in.sh + ((size_t)scene * d.P + g0) * (size_t)sh_n, s_dsh + (size_t)warp * 32 * row_stride,
-                          min(32, d.P - g0), sh_n, row_stride, lane);
-            __syncwarp();
+            const float2 t = vgr.d_mean2d[vg];
+            m2[0] = t.x; m2[1] = t.y;
         }
         if (!vis) continue;
         const float *__restrict__ vm = in.view + 16 * vid;
@@ -144,9 +150,9 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
                     const int idx = sh_index(layout, M, k, ch);
-                    const float coef = staged_in_place ? row[idx] : __ldg(sh + idx);
+                    const float coef = row[idx];
                     const float val = Y * dl[ch];
-                    row[idx] = first ? val : row[idx] + val;
+                    grow[idx] = first ? val : grow[idx] + val;
                     const float cd = coef * dl[ch];
                     dLdx += Yx * cd; dLdy += Yy * cd; dLdz += Yz * cd;
                 }
@@ -154,7 +160,7 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
             if (first) {
                 const int nb = (d.deg + 1) * (d.deg + 1);
                 for (int k = nb; k < M; ++k)
-                    for (int ch = 0; ch < 3; ++ch) row[sh_index(layout, M, k, ch)] = 0.0f;
+                    for (int ch = 0; ch < 3; ++ch) grow[sh_index(layout, M, k, ch)] = 0.0f;
             }
             sh_written = true;
             const float inv3 = 1.0f / (len2 * len);
@@ -176,8 +182,7 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
             for (int i = 0; i < 6; ++i) dc[i] = dcov[i];
         } else {
             dc[0] = dcov[0]; dc[1] = dcov[1]; dc[2] = dcov[2];
-            dc[3] = 0.0f;    dc[4] = dcov[3]; dc[5] = dcov[4];
-            dc[6] = 0.0f;    dc[7] = 0.0f;    dc[8] = dcov[5];
+            dc[4] = dcov[3]; dc[5] = dcov[4]; dc[8] = dcov[5];      // lower triangle stays zero (pre-filled)
         }
         if (M == 0) {
             float *dsh = out.d_sh + sg * 3;
@@ -185,29 +190,44 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
         }
     }
     if (M > 0) {
-        // rows that received nothing (culled in every view) are zero-filled by their own lane, then
-        // the warp writes its 32 rows out as one contiguous coalesced run
-        if (!sh_written)
-            for (int i = 0; i < sh_n; ++i) row[i] = 0.0f;
+        // every listed Gaussian is visible in >= 1 view, so its gradient row was written above
         __syncwarp();
-        const int rows = min(32, d.P - g0);
-        if (rows > 0)
-            unstage_sh_rows(s_dsh + (size_t)warp * 32 * row_stride,
-                            out.d_sh + ((size_t)scene * d.P + g0) * (size_t)sh_n, rows, sh_n, row_stride, lane);
+        const float *gsrc = in_place ? wrows : wrows + (size_t)kPreBwdThreads * row_stride;
+        for (int r = 0; r < 32; ++r) {
+            const size_t rsg = __shfl_sync(0xffffffffu, (unsigned long long)sg, r);
+            if (i0 + r < n) {
+                float *__restrict__ dst = out.d_sh + rsg * (size_t)sh_n;
+                for (int c = lane; c < sh_n; c += 32) dst[c] = gsrc[r * row_stride + c];
+            }
+        }
     }
+}
+
+// Zero gradients for everything the dense kernel does not write (Gaussians that are on screen in
+// no view, the lower covariance triangle, optional screen-space gradients).  Pure memsets.
+int launch_gradient_fill(const Dims &d, const ps_raster_grads &out, cudaStream_t st) {
+    const size_t sp = (size_t)d.S * d.P;
+    PS_CUDA_CHECK(cudaMemsetAsync(out.d_means, 0, sp * 3 * sizeof(float), st));
+    PS_CUDA_CHECK(cudaMemsetAsync(out.d_cov, 0, sp * (d.cov_layout == PS_COV_TRIU6 ? 6 : 9) * sizeof(float), st));
+    PS_CUDA_CHECK(cudaMemsetAsync(out.d_opacities, 0, sp * sizeof(float), st));
+    PS_CUDA_CHECK(cudaMemsetAsync(out.d_sh, 0, sp * (d.M > 0 ? 3 * d.M : 3) * sizeof(float), st));
+    if (out.d_means2d)
+        PS_CUDA_CHECK(cudaMemsetAsync(out.d_means2d, 0, (size_t)d.S * d.V * d.P * 3 * sizeof(float), st));
+    return PS_OK;
 }
 
 int launch_preprocess_backward(const Dims &d, const Inputs &in, const Geom &g, const ViewGrads &vg,
                                const ps_raster_grads &out, cudaStream_t st) {
-    dim3 grid((d.P + kPreBwdThreads - 1) / kPreBwdThreads, d.S);
     const int row_stride = d.M > 0 ? ((3 * d.M) | 1) : 1;   // odd word count: conflict-free per-lane rows
-    const size_t smem = d.M > 0 ? sizeof(float) * kPreBwdThreads * row_stride : 0;
+    const size_t smem = d.M > 0 ? sizeof(float) * kPreBwdThreads * row_stride * (d.V == 1 ? 1 : 2) : 0;
     static bool attr = false;
     if (!attr) {
-        PS_CUDA_CHECK(cudaFuncSetAttribute(k_preprocess_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        PS_CUDA_CHECK(cudaFuncSetAttribute(k_preprocess_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr = true;
     }
-    k_preprocess_bwd<<<grid, kPreBwdThreads, smem, st>>>(d, in, g, vg, out, row_stride);
+    const long long sp = (long long)d.S * d.P;               // worst case; surplus warps exit at once
+    k_preprocess_bwd<<<(unsigned)((sp + kPreBwdThreads - 1) / kPreBwdThreads), kPreBwdThreads, smem, st>>>(
+        d, in, g, vg, out, row_stride);
     PS_LAUNCH_CHECK("k_preprocess_bwd");
     return PS_OK;
 }

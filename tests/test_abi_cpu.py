@@ -57,7 +57,7 @@ def test_sizes_layout_and_validation_without_gpu():
     assert lay.depth == 0 and lay.radii >= vp * 4 and lay.keys == 0 and lay.keys_alt >= 12345 * 8
     assert s.binning_bytes >= 2 * 12345 * 8 and s.image_bytes >= 2 * 6 * 70 * 50 * 4
     assert s.backward_bytes >= vp * 40
-    offs = [getattr(lay, f) for f, _ in _lib.RasterLayout._fields_[:11]]
+    offs = [getattr(lay, f) for f, _ in _lib.RasterLayout._fields_[:13]]
     assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
     assert lay.tile_start - lay.tile_count >= 6 * tiles * 4
     for field, bad in (("n_gaussians", 0), ("sh_degree", 5), ("sh_coeffs", 26), ("sh_layout", 7),
