@@ -73,6 +73,7 @@ void count_launch();
 
 // stage launchers (each returns PS_OK / PS_ERR_*)
 int launch_preprocess(const Dims &d, const Inputs &in, const Geom &g, cudaStream_t st);
+int launch_sh_color(const Dims &d, const Inputs &in, const Geom &g, cudaStream_t st);
 int launch_binning(const Dims &d, const Geom &g, unsigned long long *keys,
                    unsigned long long *keys_alt, int sort_impl, int segment_hint, cudaStream_t st);
 int launch_composite_forward(const Dims &d, const Inputs &in, const Geom &g,

@@ -245,10 +245,18 @@ PS_API int ps_raster_forward(const ps_raster_desc *desc, const ps_raster_inputs 
     uint32_t *n_contrib = reinterpret_cast<uint32_t *>(static_cast<char *>(state->image) + L.off.n_contrib);
 
     mark(kMarkFwdStart, st);
+    if ((rc = side_ready())) return rc;
     if ((rc = launch_preprocess(d, I, g, st))) return rc;
     mark(kMarkPreprocess, st);
+    // fork: SH -> RGB of the on-screen Gaussians runs beside the binning (scan / scatter / sort);
+    // the two only meet again in the compositor
+    PS_CUDA_CHECK(cudaEventRecord(g_fork, st));
+    PS_CUDA_CHECK(cudaStreamWaitEvent(g_side, g_fork, 0));
+    if ((rc = launch_sh_color(d, I, g, g_side))) return rc;
+    PS_CUDA_CHECK(cudaEventRecord(g_join, g_side));
     if ((rc = launch_binning(d, g, keys, keys_alt, desc->sort_impl, desc->sort_segment_hint, st))) return rc;
     mark(kMarkSort, st);
+    PS_CUDA_CHECK(cudaStreamWaitEvent(st, g_join, 0));   // join
     if (n_instances_host)
         PS_CUDA_CHECK(cudaMemcpyAsync(n_instances_host, g.n_instances, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     if ((rc = launch_composite_forward(d, I, g, keys, final_T, n_contrib, out_color, st))) return rc;

@@ -191,6 +191,22 @@ k_sh_color(Dims d, Inputs in, Geom geo, int row_stride) {
     geo.clamped[vg] = clamp_bits;
 }
 
+int launch_sh_color(const Dims &d, const Inputs &in, const Geom &g, cudaStream_t st) {
+    if (d.M == 0) return PS_OK;
+    // the pair count lives on the device: launch for the worst case, surplus warps exit at once
+    const int row_stride = (3 * d.M) | 1;
+    const size_t smem = sizeof(float) * kShThreads * row_stride;
+    static bool attr = false;
+    if (!attr) {
+        PS_CUDA_CHECK(cudaFuncSetAttribute(k_sh_color, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr = true;
+    }
+    const long long pairs = (long long)d.S * d.V * d.P;
+    k_sh_color<<<(unsigned)((pairs + kShThreads - 1) / kShThreads), kShThreads, smem, st>>>(d, in, g, row_stride);
+    PS_LAUNCH_CHECK("k_sh_color");
+    return PS_OK;
+}
+
 int launch_preprocess(const Dims &d, const Inputs &in, const Geom &g, cudaStream_t st) {
     PS_CUDA_CHECK(cudaMemsetAsync(g.tile_count, 0, sizeof(uint32_t) * (size_t)d.S * d.V * d.tiles, st));
     PS_CUDA_CHECK(cudaMemsetAsync(g.n_instances, 0, 4 * sizeof(long long), st));
@@ -199,19 +215,6 @@ int launch_preprocess(const Dims &d, const Inputs &in, const Geom &g, cudaStream
     dim3 grid((d.P + kPreThreads - 1) / kPreThreads, d.S);
     k_preprocess<<<grid, kPreThreads, use_smem ? hist_bytes : 0, st>>>(d, in, g, use_smem);
     PS_LAUNCH_CHECK("k_preprocess");
-    if (d.M > 0) {
-        // the pair count lives on the device: launch for the worst case, surplus warps exit at once
-        const int row_stride = (3 * d.M) | 1;
-        const size_t smem = sizeof(float) * kShThreads * row_stride;
-        static bool attr = false;
-        if (!attr) {
-            PS_CUDA_CHECK(cudaFuncSetAttribute(k_sh_color, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            attr = true;
-        }
-        const long long pairs = (long long)d.S * d.V * d.P;
-        k_sh_color<<<(unsigned)((pairs + kShThreads - 1) / kShThreads), kShThreads, smem, st>>>(d, in, g, row_stride);
-        PS_LAUNCH_CHECK("k_sh_color");
-    }
     return PS_OK;
 }
 
