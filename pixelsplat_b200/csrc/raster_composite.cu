@@ -31,6 +31,32 @@ __device__ __forceinline__ float2 alpha_extent(const float4 co) {
     return make_float2(sqrtf(inv * C) * 1.001f + 0.01f, sqrtf(inv * A) * 1.001f + 0.01f);
 }
 
+// Second-stage cull, evaluated by one lane per staged entry that passed the bounding-box test:
+// the exact minimum of the (pre-scaled) quadratic form over the warp's pixel rectangle, i.e. the
+// largest alpha any pixel of the rectangle can see.  The box test alone lets ~13 % more
+// (warp, Gaussian) pairs through than needed (elongated splats clipping a corner of the box).
+// `co` is the staged conic (qa, qb, qc <= 0 form, opacity).  Conservative: returns true when unsure.
+__device__ __forceinline__ bool rect_can_contribute(const float2 c, const float4 co, float rx0, float rx1,
+                                                    float ry0, float ry1) {
+    const float a = -co.x, b = -co.y, cc = -co.z;            // q(x, y) = a x^2 + cc y^2 + b x y = -power*log2e
+    if (!(a > 0.0f) || !(cc > 0.0f) || !(4.0f * a * cc - b * b > 0.0f)) return true;
+    const float x0 = rx0 - c.x, x1 = rx1 - c.x, y0 = ry0 - c.y, y1 = ry1 - c.y;
+    if (x0 <= 0.0f && x1 >= 0.0f && y0 <= 0.0f && y1 >= 0.0f) return true;     // centre inside
+    const float kx = -0.5f * __fdividef(b, a), ky = -0.5f * __fdividef(b, cc);
+    float qmin = 3.0e38f;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const float y = e ? y1 : y0;
+        const float x = fminf(fmaxf(kx * y, x0), x1);
+        qmin = fminf(qmin, a * x * x + cc * y * y + b * x * y);
+        const float xe = e ? x1 : x0;
+        const float ye = fminf(fmaxf(ky * xe, y0), y1);
+        qmin = fminf(qmin, a * xe * xe + cc * ye * ye + b * xe * ye);
+    }
+    // alpha >= 1/255  <=>  q <= log2(255 * opacity); small slack for the approximate exp2 / rounding
+    return qmin <= __log2f(fmaxf(255.0f * co.w, 1.0f)) + 0.03f;
+}
+
 // Shared-memory staging is SoA so that both the lane-varying cull reads (8 B stride) and the
 // broadcast reads of the evaluation loop are bank-conflict free.
 struct StageBuf {
@@ -97,6 +123,7 @@ k_composite_fwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                 if (j < n_here) {
                     const float2 c = s.xy[j], e = s.ext[j];
                     hit = (c.x + e.x >= rx0) && (c.x - e.x <= rx1) && (c.y + e.y >= ry0) && (c.y - e.y <= ry1);
+                    if (hit) hit = rect_can_contribute(c, s.co[j], rx0, rx1, ry0, ry1);
                 }
                 uint32_t mask = __ballot_sync(0xffffffffu, hit);
                 // four entries per iteration: their power / exp evaluations are independent, only
@@ -312,6 +339,7 @@ k_composite_bwd(Dims d, Geom geo, const float *__restrict__ bg_all,
             if (j < n_here && (hi - 1u - j) < warp_last) {
                 const float2 c = s.xy[j], e = s.ext[j];
                 hit = (c.x + e.x >= rx0) && (c.x - e.x <= rx1) && (c.y + e.y >= ry0) && (c.y - e.y <= ry1);
+                if (hit) hit = rect_can_contribute(c, s.co[j], rx0, rx1, ry0, ry1);
             }
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
             // four list entries per iteration: their exp / gradient math is independent (only the

@@ -172,6 +172,52 @@ __device__ __forceinline__ void unstage_sh_rows(const float *src, float *__restr
     }
 }
 
+// Gather 32 scattered rows (one per lane's Gaussian, `row_of_lane` = flat row index held by each
+// lane) of sh_n floats into the warp's shared staging area, row-wise coalesced.  Rows are
+// processed four at a time so that 4 x ceil(sh_n/32) loads are in flight before the first store.
+__device__ __forceinline__ void gather_rows(const float *__restrict__ base, unsigned long long row_of_lane,
+                                            int rows_valid, int sh_n, float *wrows, int row_stride, int lane) {
+    for (int r0 = 0; r0 < rows_valid; r0 += 4) {
+        float v[4][3];
+        const float *src[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const unsigned long long rs = __shfl_sync(0xffffffffu, row_of_lane, min(r0 + q, 31));
+            src[q] = base + rs * (unsigned long long)sh_n;
+        }
+        if (sh_n <= 96) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const int c = lane + 32 * t;
+                    v[q][t] = (r0 + q < rows_valid && c < sh_n) ? __ldg(src[q] + c) : 0.0f;
+                }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const int c = lane + 32 * t;
+                    if (r0 + q < rows_valid && c < sh_n) wrows[(r0 + q) * row_stride + c] = v[q][t];
+                }
+        } else {
+            for (int q = 0; q < 4; ++q)
+                if (r0 + q < rows_valid)
+                    for (int c = lane; c < sh_n; c += 32) wrows[(r0 + q) * row_stride + c] = __ldg(src[q] + c);
+        }
+    }
+}
+
+// The inverse: write the warp's staged rows back to their scattered global rows.
+__device__ __forceinline__ void scatter_rows(float *__restrict__ base, unsigned long long row_of_lane,
+                                             int rows_valid, int sh_n, const float *wrows, int row_stride, int lane) {
+    for (int r = 0; r < rows_valid; ++r) {
+        const unsigned long long rs = __shfl_sync(0xffffffffu, row_of_lane, r);
+        float *__restrict__ dst = base + rs * (unsigned long long)sh_n;
+        for (int c = lane; c < sh_n; c += 32) dst[c] = wrows[r * row_stride + c];
+    }
+}
+
 __device__ __forceinline__ int sh_index(int layout, int M, int k, int ch) {
     return layout == PS_SH_M3 ? k * 3 + ch : ch * M + k;
 }

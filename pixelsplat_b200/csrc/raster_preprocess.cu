@@ -152,14 +152,7 @@ k_sh_color(Dims d, Inputs in, Geom geo, int row_stride) {
     const size_t sg = (size_t)scene * d.P + g;
     const int sh_n = 3 * d.M;
     float *wrows = s_rows + (size_t)warp * 32 * row_stride;
-    // cooperative row loads: lane l fetches floats l, l+32, ... of every row
-    for (int r = 0; r < 32; ++r) {
-        const size_t rsg = __shfl_sync(0xffffffffu, (unsigned long long)sg, r);
-        if (i0 + r < n) {
-            const float *__restrict__ src = in.sh + rsg * (size_t)sh_n;
-            for (int c = lane; c < sh_n; c += 32) wrows[r * row_stride + c] = __ldg(src + c);
-        }
-    }
+    gather_rows(in.sh, (unsigned long long)sg, (int)min((long long)32, n - i0), sh_n, wrows, row_stride, lane);
     __syncwarp();
     if (!live) return;
     const float sc = in.scale ? in.scale[vid] : 1.0f;

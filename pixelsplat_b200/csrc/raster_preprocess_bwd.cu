@@ -40,14 +40,9 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
     const bool in_place = M > 0 && d.V == 1;     // read each coefficient, then overwrite its slot with the gradient
     float *grow = in_place ? row : row + (size_t)kPreBwdThreads * row_stride;   // separate gradient rows when V > 1
 
+    const int rows_valid = (int)min((long long)32, n - i0);
     if (M > 0) {
-        for (int r = 0; r < 32; ++r) {
-            const size_t rsg = __shfl_sync(0xffffffffu, (unsigned long long)sg, r);
-            if (i0 + r < n) {
-                const float *__restrict__ src = in.sh + rsg * (size_t)sh_n;
-                for (int c = lane; c < sh_n; c += 32) wrows[r * row_stride + c] = __ldg(src + c);
-            }
-        }
+        gather_rows(in.sh, (unsigned long long)sg, rows_valid, sh_n, wrows, row_stride, lane);
         __syncwarp();
     }
 
@@ -193,13 +188,7 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
         // every listed Gaussian is visible in >= 1 view, so its gradient row was written above
         __syncwarp();
         const float *gsrc = in_place ? wrows : wrows + (size_t)kPreBwdThreads * row_stride;
-        for (int r = 0; r < 32; ++r) {
-            const size_t rsg = __shfl_sync(0xffffffffu, (unsigned long long)sg, r);
-            if (i0 + r < n) {
-                float *__restrict__ dst = out.d_sh + rsg * (size_t)sh_n;
-                for (int c = lane; c < sh_n; c += 32) dst[c] = gsrc[r * row_stride + c];
-            }
-        }
+        scatter_rows(out.d_sh, (unsigned long long)sg, rows_valid, sh_n, gsrc, row_stride, lane);
     }
 }
 
