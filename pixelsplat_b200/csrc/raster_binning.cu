@@ -334,18 +334,22 @@ k_tile_sort_radix11(const uint32_t *__restrict__ tile_start, const uint32_t *__r
             __syncwarp();
         }
         __syncthreads();
-        {   // column sums -> per-(warp, digit) start offsets; thread t owns digits 8t .. 8t+7
+        {   // column sums -> per-(warp, digit) start offsets; thread t owns digits 8t .. 8t+7.
+            // All 64 counters are loaded first (independent 16-byte loads: 8 consecutive u16 per
+            // warp row) so the shared-memory latency is paid once, not 64 times in a chain.
+            uint32_t c[kR11Warps][8];
+#pragma unroll
+            for (int w = 0; w < kR11Warps; ++w) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(cnt + w * kR11Bins + 8 * tid);
+                c[w][0] = v.x & 0xffffu; c[w][1] = v.x >> 16; c[w][2] = v.y & 0xffffu; c[w][3] = v.y >> 16;
+                c[w][4] = v.z & 0xffffu; c[w][5] = v.z >> 16; c[w][6] = v.w & 0xffffu; c[w][7] = v.w >> 16;
+            }
             uint32_t tot[8], sum = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int dg = 8 * tid + j;
                 uint32_t run = 0;
 #pragma unroll
-                for (int w = 0; w < kR11Warps; ++w) {
-                    const uint32_t c = cnt[w * kR11Bins + dg];
-                    cnt[w * kR11Bins + dg] = (uint16_t)run;
-                    run += c;
-                }
+                for (int w = 0; w < kR11Warps; ++w) { const uint32_t t = c[w][j]; c[w][j] = run; run += t; }
                 tot[j] = run;
                 sum += run;
             }
@@ -361,10 +365,16 @@ k_tile_sort_radix11(const uint32_t *__restrict__ tile_start, const uint32_t *__r
             for (int w = 0; w < warp; ++w) run2 += misc[8 + w];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int dg = 8 * tid + j;
 #pragma unroll
-                for (int w = 0; w < kR11Warps; ++w) cnt[w * kR11Bins + dg] = (uint16_t)(cnt[w * kR11Bins + dg] + run2);
+                for (int w = 0; w < kR11Warps; ++w) c[w][j] += run2;
                 run2 += tot[j];
+            }
+#pragma unroll
+            for (int w = 0; w < kR11Warps; ++w) {
+                uint4 v;
+                v.x = c[w][0] | (c[w][1] << 16); v.y = c[w][2] | (c[w][3] << 16);
+                v.z = c[w][4] | (c[w][5] << 16); v.w = c[w][6] | (c[w][7] << 16);
+                *reinterpret_cast<uint4 *>(cnt + w * kR11Bins + 8 * tid) = v;
             }
         }
         __syncthreads();

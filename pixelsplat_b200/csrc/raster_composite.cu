@@ -31,32 +31,6 @@ __device__ __forceinline__ float2 alpha_extent(const float4 co) {
     return make_float2(sqrtf(inv * C) * 1.001f + 0.01f, sqrtf(inv * A) * 1.001f + 0.01f);
 }
 
-// Second-stage cull, evaluated by one lane per staged entry that passed the bounding-box test:
-// the exact minimum of the (pre-scaled) quadratic form over the warp's pixel rectangle, i.e. the
-// largest alpha any pixel of the rectangle can see.  The box test alone lets ~13 % more
-// (warp, Gaussian) pairs through than needed (elongated splats clipping a corner of the box).
-// `co` is the staged conic (qa, qb, qc <= 0 form, opacity).  Conservative: returns true when unsure.
-__device__ __forceinline__ bool rect_can_contribute(const float2 c, const float4 co, float rx0, float rx1,
-                                                    float ry0, float ry1) {
-    const float a = -co.x, b = -co.y, cc = -co.z;            // q(x, y) = a x^2 + cc y^2 + b x y = -power*log2e
-    if (!(a > 0.0f) || !(cc > 0.0f) || !(4.0f * a * cc - b * b > 0.0f)) return true;
-    const float x0 = rx0 - c.x, x1 = rx1 - c.x, y0 = ry0 - c.y, y1 = ry1 - c.y;
-    if (x0 <= 0.0f && x1 >= 0.0f && y0 <= 0.0f && y1 >= 0.0f) return true;     // centre inside
-    const float kx = -0.5f * __fdividef(b, a), ky = -0.5f * __fdividef(b, cc);
-    float qmin = 3.0e38f;
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-        const float y = e ? y1 : y0;
-        const float x = fminf(fmaxf(kx * y, x0), x1);
-        qmin = fminf(qmin, a * x * x + cc * y * y + b * x * y);
-        const float xe = e ? x1 : x0;
-        const float ye = fminf(fmaxf(ky * xe, y0), y1);
-        qmin = fminf(qmin, a * xe * xe + cc * ye * ye + b * xe * ye);
-    }
-    // alpha >= 1/255  <=>  q <= log2(255 * opacity); small slack for the approximate exp2 / rounding
-    return qmin <= __log2f(fmaxf(255.0f * co.w, 1.0f)) + 0.03f;
-}
-
 // Shared-memory staging is SoA so that both the lane-varying cull reads (8 B stride) and the
 // broadcast reads of the evaluation loop are bank-conflict free.
 struct StageBuf {
@@ -79,12 +53,30 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
-__device__ __forceinline__ void stage_entry(StageBuf &s, int slot, const Geom &geo, size_t base, uint32_t g) {
-    const float4 co = geo.conic_opacity[base + g];
-    s.xy[slot] = geo.xy[base + g];
-    s.co[slot] = make_float4(-0.5f * kLog2e * co.x, -kLog2e * co.y, -0.5f * kLog2e * co.z, co.w);
-    s.rgb[slot] = geo.rgb[base + g];
-    s.ext[slot] = alpha_extent(co);
+// Staging is software-pipelined: the gathers of round r+1 (key -> xy / conic / rgb, two dependent
+// L2 round trips) are issued into registers before round r is processed and only parked in shared
+// memory at the top of the next iteration, so their latency hides behind the composite math
+// instead of stalling all 8 warps of the CTA once per 256 entries.
+struct StagedRegs {
+    float2 xy;
+    float4 co, rgb;
+    uint32_t g;
+};
+
+__device__ __forceinline__ StagedRegs stage_load(const Geom &geo, size_t base, uint32_t g) {
+    StagedRegs r;
+    r.g = g;
+    r.xy = geo.xy[base + g];
+    r.co = geo.conic_opacity[base + g];
+    r.rgb = geo.rgb[base + g];
+    return r;
+}
+
+__device__ __forceinline__ void stage_store(StageBuf &s, int slot, const StagedRegs &r) {
+    s.xy[slot] = r.xy;
+    s.co[slot] = make_float4(-0.5f * kLog2e * r.co.x, -kLog2e * r.co.y, -0.5f * kLog2e * r.co.z, r.co.w);
+    s.rgb[slot] = r.rgb;
+    s.ext[slot] = alpha_extent(r.co);
 }
 
 __global__ void __launch_bounds__(kCompThreads)
@@ -111,11 +103,16 @@ k_composite_fwd(Dims d, Geom geo, const float *__restrict__ bg_all,
     bool done = !inside;
     bool warp_done = __all_sync(0xffffffffu, done);
 
+    StagedRegs nxt;
+    nxt.g = 0; nxt.xy = make_float2(0.0f, 0.0f); nxt.co = nxt.rgb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if ((uint32_t)tid < count) nxt = stage_load(geo, gbase, (uint32_t)keys[start + tid]);
     for (uint32_t round0 = 0; round0 < count; round0 += kStage) {
         if (__syncthreads_count(warp_done ? 1 : 0) == kCompThreads) break;
         const uint32_t n_here = min((uint32_t)kStage, count - round0);
-        if ((uint32_t)tid < n_here) stage_entry(s, tid, geo, gbase, (uint32_t)keys[start + round0 + tid]);
+        if ((uint32_t)tid < n_here) stage_store(s, tid, nxt);
         __syncthreads();
+        if (round0 + kStage + (uint32_t)tid < count)         // prefetch the next round
+            nxt = stage_load(geo, gbase, (uint32_t)keys[start + round0 + kStage + tid]);
         if (!warp_done) {
             for (uint32_t jb = 0; jb < n_here; jb += 32) {
                 const uint32_t j = jb + lane;
@@ -123,7 +120,6 @@ k_composite_fwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                 if (j < n_here) {
                     const float2 c = s.xy[j], e = s.ext[j];
                     hit = (c.x + e.x >= rx0) && (c.x - e.x <= rx1) && (c.y + e.y >= ry0) && (c.y - e.y <= ry1);
-                    if (hit) hit = rect_can_contribute(c, s.co[j], rx0, rx1, ry0, ry1);
                 }
                 uint32_t mask = __ballot_sync(0xffffffffu, hit);
                 // four entries per iteration: their power / exp evaluations are independent, only
@@ -323,14 +319,18 @@ k_composite_bwd(Dims d, Geom geo, const float *__restrict__ bg_all,
     st.acc_r = st.acc_g = st.acc_b = st.last_alpha = st.lc_r = st.lc_g = st.lc_b = 0.0f;
 
     // walk positions block_last-1 .. 0, staged in chunks of kStage (highest position first)
+    StagedRegs nxt;
+    nxt.g = 0; nxt.xy = make_float2(0.0f, 0.0f); nxt.co = nxt.rgb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if ((uint32_t)tid < block_last) nxt = stage_load(geo, gbase, (uint32_t)keys[start + (block_last - 1u - (uint32_t)tid)]);
     for (uint32_t hi = block_last; hi > 0;) {
         const uint32_t n_here = min((uint32_t)kStage, hi);
         // staged index j <-> list position  pos = hi - 1 - j
         if ((uint32_t)tid < n_here) {
-            const uint32_t g = (uint32_t)keys[start + (hi - 1u - (uint32_t)tid)];
-            stage_entry(s, tid, geo, gbase, g);
-            s_g[tid] = g;
+            stage_store(s, tid, nxt);
+            s_g[tid] = nxt.g;
         }
+        if (hi > n_here && (uint32_t)tid < hi - n_here)      // prefetch the next (lower) chunk
+            nxt = stage_load(geo, gbase, (uint32_t)keys[start + (hi - n_here - 1u - (uint32_t)tid)]);
         for (int i = tid; i < (kCompThreads / 32) * kStage * 10; i += kCompThreads) s_acc_all[i] = 0.0f;
         __syncthreads();
         for (uint32_t jb = 0; jb < n_here; jb += 32) {
@@ -339,7 +339,6 @@ k_composite_bwd(Dims d, Geom geo, const float *__restrict__ bg_all,
             if (j < n_here && (hi - 1u - j) < warp_last) {
                 const float2 c = s.xy[j], e = s.ext[j];
                 hit = (c.x + e.x >= rx0) && (c.x - e.x <= rx1) && (c.y + e.y >= ry0) && (c.y - e.y <= ry1);
-                if (hit) hit = rect_can_contribute(c, s.co[j], rx0, rx1, ry0, ry1);
             }
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
             // four list entries per iteration: their exp / gradient math is independent (only the

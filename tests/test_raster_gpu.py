@@ -272,3 +272,63 @@ def test_idempotent_and_deterministic_forward():
     c2, r2, s2, _ = _native(a, (0, 0, 0), 128, 128)
     assert np.array_equal(c1, c2) and np.array_equal(r1, r2)
     assert torch.equal(s1.intermediates()["keys"], s2.intermediates()["keys"])
+
+
+def test_known_answers_on_the_gpu():
+    """The hand-derived cases of tests/test_oracle_raster.py, through the CUDA path: a Gaussian
+    centred on a pixel, front-to-back order of two overlapping Gaussians given far-first, the
+    z <= 0.2 cull boundary, and the four-tile corner case."""
+    from oracle import raster_torch as rt
+    from pixelsplat_b200.rasterizer import rasterize_gaussians
+    W = H = 64
+    K = torch.tensor([[0.88, 0, 0.5], [0, 0.88, 0.5], [0, 0, 1.0]])
+    vm, pm, cp, tx, ty = rt.camera_from_c2w(torch.eye(4), K, 0.5, 100.0, torch.float32)
+    C0 = 0.28209479177387814
+
+    def pt(i, j, z):
+        return [((2 * i + 1) / W - 1) * tx * z, ((2 * j + 1) / H - 1) * ty * z, z]
+
+    def iso(s):
+        return [s * s, 0, 0, s * s, 0, s * s]
+
+    def run(means, cov6, opac, sh, bg=(0.0, 0.0, 0.0)):
+        t = lambda x: torch.tensor(x, dtype=torch.float32, device=DEV)
+        states = []
+        color, radii = rasterize_gaussians(
+            t(means)[None], t(cov6)[None], t(opac)[None], t(sh)[None], viewmatrix=vm.to(DEV)[None],
+            projmatrix=pm.to(DEV)[None], campos=cp.to(DEV)[None], tanfov=t([[tx, ty]]), background=t([list(bg)]),
+            image_shape=(H, W), views_per_scene=1, sh_degree=0, state_out=states)
+        return color[0].cpu().numpy(), radii[0].cpu().numpy(), states[0].intermediates()
+
+    # one Gaussian on a pixel centre: alpha = min(0.99, opacity), colour = C0 * sh0 + 0.5
+    for opacity in (0.5, 1.0):
+        color, _, im = run([pt(20, 30, 5.0)], [iso(0.05)], [opacity], [[[1.0, -0.5, 0.2]]])
+        alpha = min(0.99, opacity)
+        expect = np.maximum(C0 * np.array([1.0, -0.5, 0.2]) + 0.5, 0) * alpha
+        assert np.allclose(color[:, 30, 20], expect, atol=1e-5)
+        assert abs(float(im["final_T"][0, 30, 20]) - (1 - alpha)) < 1e-5 and int(im["n_contrib"][0, 30, 20]) == 1
+    # two overlapping Gaussians, far one listed first
+    sh = [[[(1.0 - 0.5) / C0] * 3], [[(0.25 - 0.5) / C0] * 3]]
+    color, _, im = run([pt(10, 10, 4.0), pt(10, 10, 2.0)], [iso(0.1), iso(0.05)], [0.8, 0.6], sh, bg=(0.5, 0.5, 0.5))
+    expect = 0.25 * 0.6 + 1.0 * 0.8 * 0.4 + 0.5 * 0.4 * 0.2
+    assert np.allclose(color[:, 10, 10], expect, atol=1e-5)
+    assert (im["keys"][:2].cpu().numpy() & 0xFFFFFFFF).tolist() == [1, 0]
+    # cull boundary
+    z_above = float(np.nextafter(np.float32(0.2), np.float32(1)))
+    _, radii, _ = run([[0, 0, 0.2], [0, 0, z_above]], [iso(0.001)] * 2, [0.5, 0.5], [[[0.0] * 3]] * 2)
+    assert radii[0] == 0 and radii[1] > 0
+    # tile corner -> exactly four tiles
+    z = 5.0
+    p = [((2 * 15.5 + 1) / W - 1) * tx * z, ((2 * 15.5 + 1) / H - 1) * ty * z, z]
+    _, _, im = run([p], [iso(0.02)], [0.9], [[[0.0] * 3]])
+    assert im["num_instances"] == 4 and im["tile_count"][0].cpu().numpy().nonzero()[0].tolist() == [0, 1, 4, 5]
+
+
+def test_equal_depth_ties_are_broken_by_index():
+    """All Gaussians on one plane parallel to the image (identical depth bits): the per-tile order
+    must fall back to ascending Gaussian index -- short runs, and a run long enough (> 64) to take
+    the sort's fallback path."""
+    sc = synthetic.scene_random_frustum(seed=13, image_hw=(32, 32), num_gaussians=900)
+    sc.means[:, 2] = 3.0
+    sc.means[:300, 2] = 5.0
+    _check_forward(util.view_args(sc), (0.0, 0.0, 0.0), 32, 32)
