@@ -145,16 +145,15 @@ def capture_step(d, d_img, views):
 
 
 def algorithmic_bytes(P, M, N, vis, HW, cov_floats=9):
-    """Per-view algorithmic HBM bytes of each stage."""
+    """Per-view algorithmic HBM bytes of each timed stage."""
     return {
-        "preprocess": P * (12 + 4 * cov_floats + 4 + 4) + vis * (12 * M + 4 + 8 + 16 + 16 + 8 + 1),
+        "preprocess": P * (12 + 4 * cov_floats + 4 + 4) + vis * 41,        # k_preprocess (k_sh_color overlaps binning)
         "count_scan_scatter": P * 4 + vis * (8 + 4) + N * 8,
-        "tile_sort": N * 16,
+        "tile_sort": N * 16 + vis * (12 * M + 12 + 17),                     # sort + the concurrent k_sh_color
         "composite_fwd": N * (8 + 8 + 16 + 16) + HW * 20,
         "grad_zero_fill": P * 40,
         "composite_bwd": N * (8 + 8 + 16 + 16) + N * 36 + HW * 20,
-        "preprocess_bwd": P * (12 + 4 * cov_floats + 4) + vis * (40 + 12 * M) +
-                          P * (12 + 4 * cov_floats + 4 + 12 * M),
+        "preprocess_bwd": vis * (52 + 40 + 12 * M) + vis * (52 + 12 * M),
     }
 
 

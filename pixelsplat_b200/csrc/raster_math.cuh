@@ -177,33 +177,34 @@ __device__ __forceinline__ void unstage_sh_rows(const float *src, float *__restr
 // processed four at a time so that 4 x ceil(sh_n/32) loads are in flight before the first store.
 __device__ __forceinline__ void gather_rows(const float *__restrict__ base, unsigned long long row_of_lane,
                                             int rows_valid, int sh_n, float *wrows, int row_stride, int lane) {
-    for (int r0 = 0; r0 < rows_valid; r0 += 4) {
-        float v[4][3];
-        const float *src[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const unsigned long long rs = __shfl_sync(0xffffffffu, row_of_lane, min(r0 + q, 31));
-            src[q] = base + rs * (unsigned long long)sh_n;
-        }
+    constexpr int kBatch = 8;        // rows per batch: 8 x ceil(sh_n/32) <= 24 loads in flight per lane
+    for (int r0 = 0; r0 < rows_valid; r0 += kBatch) {
         if (sh_n <= 96) {
+            float v[kBatch][3];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < kBatch; ++q) {
+                const unsigned long long rs = __shfl_sync(0xffffffffu, row_of_lane, min(r0 + q, 31));
+                const float *src = base + rs * (unsigned long long)sh_n;
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
                     const int c = lane + 32 * t;
-                    v[q][t] = (r0 + q < rows_valid && c < sh_n) ? __ldg(src[q] + c) : 0.0f;
+                    v[q][t] = (r0 + q < rows_valid && c < sh_n) ? __ldg(src + c) : 0.0f;
                 }
+            }
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < kBatch; ++q)
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
                     const int c = lane + 32 * t;
                     if (r0 + q < rows_valid && c < sh_n) wrows[(r0 + q) * row_stride + c] = v[q][t];
                 }
         } else {
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < kBatch; ++q) {
+                const unsigned long long rs = __shfl_sync(0xffffffffu, row_of_lane, min(r0 + q, 31));
                 if (r0 + q < rows_valid)
-                    for (int c = lane; c < sh_n; c += 32) wrows[(r0 + q) * row_stride + c] = __ldg(src[q] + c);
+                    for (int c = lane; c < sh_n; c += 32)
+                        wrows[(r0 + q) * row_stride + c] = __ldg(base + rs * (unsigned long long)sh_n + c);
+            }
         }
     }
 }
