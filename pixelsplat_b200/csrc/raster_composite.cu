@@ -268,6 +268,81 @@ __device__ __forceinline__ bool pixel_bwd(bool in_range, const float2 exy, const
     return active;
 }
 
+// Two list entries at once with Blackwell's packed FP32x2 arithmetic (FADD2 / FMUL2 / FFMA2,
+// sm_100 only: one issue slot, two results).  Everything that is element-wise per entry -- the
+// quadratic form, alpha, the gradient terms -- is evaluated on (entry a, entry b) register pairs;
+// the short per-pixel recurrences (T, colour behind) stay scalar and run a then b, exactly as the
+// list order demands.  The composite backward is issue-bound (63 % issue-active at 14 warps/SM,
+// profiles/r01_ncu_metrics_v10.csv), so instructions saved are time saved.
+__device__ __forceinline__ float2 pk(float a, float b) { return make_float2(a, b); }
+
+__device__ __forceinline__ void pixel_bwd_pair(bool in_a, bool in_b, const float2 xya, const float2 xyb,
+                                               const float4 coa, const float4 cob, const float4 ca,
+                                               const float4 cb, float px, float py, float dpr, float dpg,
+                                               float dpb, float T_final, float bg_dot, float kx, float ky,
+                                               PixelState &st, float *ga, float *gb, float &opa, float &opb,
+                                               bool &act_a, bool &act_b) {
+    const float2 DX = __fadd2_rn(pk(xya.x, xyb.x), pk(-px, -px));
+    const float2 DY = __fadd2_rn(pk(xya.y, xyb.y), pk(-py, -py));
+    const float2 QA = pk(coa.x, cob.x), QB = pk(coa.y, cob.y), QC = pk(coa.z, cob.z), W = pk(coa.w, cob.w);
+    float2 P = __fmul2_rn(__fmul2_rn(QA, DX), DX);
+    P = __ffma2_rn(__fmul2_rn(QC, DY), DY, P);
+    P = __ffma2_rn(__fmul2_rn(QB, DX), DY, P);                       // power * log2(e), both entries
+    const float2 G = pk(fast_exp2(P.x), fast_exp2(P.y));
+    const float2 AL = __fmul2_rn(W, G);
+    const float al_a = fminf(0.99f, AL.x), al_b = fminf(0.99f, AL.y);
+    act_a = in_a && !(P.x > 0.0f) && !(al_a < kAlphaMin);
+    act_b = in_b && !(P.y > 0.0f) && !(al_b < kAlphaMin);
+    // skipped entries behave like alpha = 0, G = 0 (see pixel_bwd)
+    const float2 A = pk(act_a ? al_a : 0.0f, act_b ? al_b : 0.0f);
+    const float2 GS = pk(act_a ? G.x : 0.0f, act_b ? G.y : 0.0f);
+    const float2 OM = __fadd2_rn(pk(1.0f, 1.0f), pk(-A.x, -A.y));
+    const float rcp_a = __fdividef(1.0f, OM.x), rcp_b = __fdividef(1.0f, OM.y);
+    // ---- entry a, then entry b: transmittance and colour-behind recurrences (scalar / channel-packed)
+    const float Ta = st.T * rcp_a;
+    float2 acc_rg = pk(st.acc_r, st.acc_g);
+    float acc_b_ = st.acc_b;
+    {
+        const float la = st.last_alpha;
+        acc_rg = __ffma2_rn(pk(la, la), __fadd2_rn(pk(st.lc_r, st.lc_g), pk(-acc_rg.x, -acc_rg.y)), acc_rg);
+        acc_b_ = acc_b_ + la * (st.lc_b - acc_b_);
+    }
+    const float2 da_rg = __fadd2_rn(pk(ca.x, ca.y), pk(-acc_rg.x, -acc_rg.y));
+    const float2 ta_rg = __fmul2_rn(da_rg, pk(dpr, dpg));
+    float dLa = ta_rg.x + ta_rg.y + (ca.z - acc_b_) * dpb;
+    dLa = dLa * Ta - T_final * rcp_a * bg_dot;
+    const float Tb = Ta * rcp_b;
+    {
+        const float la = A.x;
+        acc_rg = __ffma2_rn(pk(la, la), __fadd2_rn(pk(ca.x, ca.y), pk(-acc_rg.x, -acc_rg.y)), acc_rg);
+        acc_b_ = acc_b_ + la * (ca.z - acc_b_);
+    }
+    const float2 db_rg = __fadd2_rn(pk(cb.x, cb.y), pk(-acc_rg.x, -acc_rg.y));
+    const float2 tb_rg = __fmul2_rn(db_rg, pk(dpr, dpg));
+    float dLb = tb_rg.x + tb_rg.y + (cb.z - acc_b_) * dpb;
+    dLb = dLb * Tb - T_final * rcp_b * bg_dot;
+    st.T = Tb;
+    st.acc_r = acc_rg.x; st.acc_g = acc_rg.y; st.acc_b = acc_b_;
+    st.lc_r = cb.x; st.lc_g = cb.y; st.lc_b = cb.z;
+    st.last_alpha = A.y;
+    // ---- gradient terms, packed across the two entries
+    const float2 DL = pk(dLa, dLb);
+    const float2 WC = __fmul2_rn(A, pk(Ta, Tb));                     // alpha * T
+    const float2 CR = __fmul2_rn(WC, pk(dpr, dpr)), CG = __fmul2_rn(WC, pk(dpg, dpg)), CB = __fmul2_rn(WC, pk(dpb, dpb));
+    const float2 WG = __fmul2_rn(__fmul2_rn(W, DL), GS);             // dL/dG * G
+    const float2 SX = __fmul2_rn(WG, DX), SY = __fmul2_rn(WG, DY);
+    const float2 two = pk(2.0f, 2.0f);
+    const float2 MX = __fmul2_rn(pk(kx, kx), __ffma2_rn(__fmul2_rn(two, QA), SX, __fmul2_rn(QB, SY)));
+    const float2 MY = __fmul2_rn(pk(ky, ky), __ffma2_rn(__fmul2_rn(two, QC), SY, __fmul2_rn(QB, SX)));
+    const float2 mh = pk(-0.5f, -0.5f);
+    const float2 HX = __fmul2_rn(mh, SX), HY = __fmul2_rn(mh, SY);
+    const float2 CA = __fmul2_rn(HX, DX), CBc = __fmul2_rn(HX, DY), CC = __fmul2_rn(HY, DY);
+    const float2 OP = __fmul2_rn(GS, DL);
+    ga[0] = MX.x; ga[1] = MY.x; ga[2] = CA.x; ga[3] = CBc.x; ga[4] = CC.x; ga[5] = CR.x; ga[6] = CG.x; ga[7] = CB.x;
+    gb[0] = MX.y; gb[1] = MY.y; gb[2] = CA.y; gb[3] = CBc.y; gb[4] = CC.y; gb[5] = CR.y; gb[6] = CG.y; gb[7] = CB.y;
+    opa = OP.x; opb = OP.y;
+}
+
 __global__ void __launch_bounds__(kCompThreads)
 k_composite_bwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                 const unsigned long long *__restrict__ keys, const float *__restrict__ final_T,
@@ -358,11 +433,14 @@ k_composite_bwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                 float v[32], op[4];
                 unsigned any = 0;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const bool aq = pixel_bwd(has[q] && (hi - 1u - jx[q]) < last, s.xy[jx[q]], s.co[jx[q]], s.rgb[jx[q]],
-                                              px, py, dpr, dpg, dpb, T_final, bg_dot, ddelx_dx, ddely_dy, st,
-                                              v + 8 * q, op[q]);
-                    any |= __ballot_sync(0xffffffffu, aq) ? (1u << q) : 0u;
+                for (int q = 0; q < 4; q += 2) {
+                    bool a0, a1;
+                    pixel_bwd_pair(has[q] && (hi - 1u - jx[q]) < last, has[q + 1] && (hi - 1u - jx[q + 1]) < last,
+                                   s.xy[jx[q]], s.xy[jx[q + 1]], s.co[jx[q]], s.co[jx[q + 1]], s.rgb[jx[q]],
+                                   s.rgb[jx[q + 1]], px, py, dpr, dpg, dpb, T_final, bg_dot, kLn2 * ddelx_dx,
+                                   kLn2 * ddely_dy, st, v + 8 * q, v + 8 * q + 8, op[q], op[q + 1], a0, a1);
+                    any |= __ballot_sync(0xffffffffu, a0) ? (1u << q) : 0u;
+                    any |= __ballot_sync(0xffffffffu, a1) ? (2u << q) : 0u;
                 }
                 if (any == 0u) continue;
                 const float tot = transpose_reduce32(v, lane);      // lane 8q + k: value k of entry q

@@ -177,7 +177,8 @@ __device__ __forceinline__ void unstage_sh_rows(const float *src, float *__restr
 // processed four at a time so that 4 x ceil(sh_n/32) loads are in flight before the first store.
 __device__ __forceinline__ void gather_rows(const float *__restrict__ base, unsigned long long row_of_lane,
                                             int rows_valid, int sh_n, float *wrows, int row_stride, int lane) {
-    constexpr int kBatch = 8;        // rows per batch: 8 x ceil(sh_n/32) <= 24 loads in flight per lane
+    constexpr int kBatch = 4;        // rows per batch: 4 x ceil(sh_n/32) <= 12 loads in flight per lane
+                                     // (8 was slower: register pressure cost more occupancy than it hid latency)
     for (int r0 = 0; r0 < rows_valid; r0 += kBatch) {
         if (sh_n <= 96) {
             float v[kBatch][3];
