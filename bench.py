@@ -101,9 +101,12 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+CONTEXT_VIEWS = 2
+
+
 def make_scene(seed: int, views: int):
     from pixelsplat_b200 import synthetic
-    return synthetic.scene_re10k_like(seed=seed, image_hw=IMAGE, context_views=2,
+    return synthetic.scene_re10k_like(seed=seed, image_hw=IMAGE, context_views=CONTEXT_VIEWS,
                                       gaussians_per_pixel=3, sh_degree=4, target_views=views)
 
 
@@ -221,11 +224,15 @@ def main():
     ap.add_argument("--views", type=int, default=1, help="target views per step (one scene)")
     ap.add_argument("--pool", type=int, default=4, help="distinct scenes cycled (> L2 in total)")
     ap.add_argument("--streams", type=int, default=4, help="extra leg: steps issued over N streams")
+    ap.add_argument("--image", type=int, default=256, help="square image size (512 with --context-views 3 = configs[4])")
+    ap.add_argument("--context-views", type=int, default=2)
     ap.add_argument("--batched-views", type=int, default=4, help="extra leg: V target views per call")
     ap.add_argument("--no-graph", action="store_true", help="issue every step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    global IMAGE, CONTEXT_VIEWS
+    IMAGE, CONTEXT_VIEWS = (args.image, args.image), args.context_views
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -461,10 +468,12 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: re10k-like 2-view -> 1 target, 256x256, 3 gauss/px, "
-                                   "batch 1, rasterizer fwd+bwd (SH degree 4)",
+            "config": {"workload": ("configs[1]: re10k-like 2-view -> 1 target, 256x256, 3 gauss/px, batch 1, "
+                                    "rasterizer fwd+bwd (SH degree 4)") if (args.image, args.context_views) == (256, 2)
+                       else f"re10k-like {args.context_views}-view -> 1 target, {args.image}x{args.image}, 3 gauss/px, "
+                            "batch 1, rasterizer fwd+bwd (SH degree 4)",
                        "views_per_step": V, "gaussians": P, "parallelism": f"replicas x{world}",
-                       "l2": f"pool of {args.pool} scenes ({args.pool * 140} MB of inputs) cycled: "
+                       "l2": f"pool of {args.pool} scenes ({args.pool * P * 352 // 10**6} MB of inputs) cycled: "
                              "inputs larger than L2, no flush",
                        "capacity_check": "deferred (verified at backward)",
                        "launch": "eager python" if args.no_graph else "one CUDA graph per scene (fwd+bwd), replayed"},

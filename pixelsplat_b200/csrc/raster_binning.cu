@@ -110,120 +110,10 @@ k_scatter(Dims d, Geom geo, unsigned long long *__restrict__ keys, int use_smem)
         }
 }
 
-// ---------------------------------------------------------------- per-tile radix sort
-// One CTA per (view, tile) segment.  8-bit LSD passes over the Gaussian-index bits then the
-// depth bits; a pass whose digit is uniform over the segment is skipped.  Each warp owns a
-// contiguous slice of the segment so the pass is stable with three barriers.
-constexpr int kSortThreads = 256;
-constexpr int kSortWarps = kSortThreads / 32;
-
-__device__ __forceinline__ uint32_t digit_of(unsigned long long k, int shift) {
-    return (uint32_t)(k >> shift) & 255u;
-}
-
-// 8-bit LSD radix sort of one segment, ping-ponging through global memory (segments too long for
-// the shared-memory sort).  `s_raw` needs sort_smem_bytes(0) bytes.
-__device__ void radix8_segment(unsigned char *s_raw, int n, uint32_t s0, unsigned long long *__restrict__ keys,
-                               unsigned long long *__restrict__ keys_alt, int id_bits) {
-    static_assert(kSortThreads == 256, "one thread per 8-bit digit");
-    const int smem_cap = 0;            // always the global ping-pong
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(s_raw);                 // [kSortWarps][256]
-    uint32_t *digit_total = cnt + kSortWarps * 256;                      // [256]
-    uint32_t *misc = digit_total + 256;                                  // [16]
-    unsigned long long *sbuf = reinterpret_cast<unsigned long long *>(misc + 16);
-
-    unsigned long long *a, *b;
-    const bool in_smem = n <= smem_cap;
-    if (in_smem) {
-        a = sbuf;
-        b = sbuf + smem_cap;
-        for (int i = tid; i < n; i += kSortThreads) a[i] = keys[s0 + i];
-    } else {
-        a = keys + s0;
-        b = keys_alt + s0;
-    }
-    __syncthreads();
-
-    const int lo = (int)(((long long)n * warp) / kSortWarps);
-    const int hi = (int)(((long long)n * (warp + 1)) / kSortWarps);
-
-    for (int pass = 0; pass < 8; ++pass) {
-        // passes 0..3 -> bits [0,32) (only those below id_bits), 4..7 -> bits [32,64)
-        const int shift = pass * 8;
-        if (pass < 4 && shift >= id_bits) continue;
-        for (int i = tid; i < kSortWarps * 256; i += kSortThreads) cnt[i] = 0;
-        if (tid == 0) misc[0] = 0;
-        __syncthreads();
-        for (int i = lo + lane; i < hi; i += 32) atomicAdd(&cnt[warp * 256 + digit_of(a[i], shift)], 1u);
-        __syncthreads();
-        // column sums: thread t owns digit t
-        {
-            uint32_t total = 0;
-#pragma unroll
-            for (int w = 0; w < kSortWarps; ++w) {
-                const uint32_t c = cnt[w * 256 + tid];
-                cnt[w * 256 + tid] = total;
-                total += c;
-            }
-            digit_total[tid] = total;
-            if (total == (uint32_t)n) misc[0] = 1;  // uniform digit: nothing to do
-        }
-        __syncthreads();
-        if (misc[0]) { __syncthreads(); continue; }
-        // exclusive scan of digit_total over 256 digits (8 warps x 32)
-        {
-            const uint32_t v = digit_total[tid];
-            uint32_t x = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-                if (lane >= o) x += y;
-            }
-            if (lane == 31) misc[1 + warp] = x;
-            __syncthreads();
-            uint32_t off = 0;
-            for (int w = 0; w < warp; ++w) off += misc[1 + w];
-            const uint32_t excl = off + x - v;
-#pragma unroll
-            for (int w = 0; w < kSortWarps; ++w) cnt[w * 256 + tid] += excl;
-        }
-        __syncthreads();
-        // stable scatter of this warp's slice
-        for (int base = lo; base < hi; base += 32) {
-            const int i = base + lane;
-            const bool valid = i < hi;
-            const unsigned long long key = valid ? a[i] : 0ull;
-            const uint32_t dg = valid ? digit_of(key, shift) : (256u + (uint32_t)lane);
-            const uint32_t peers = __match_any_sync(0xffffffffu, dg);
-            const int leader = __ffs(peers) - 1;
-            const int rank = __popc(peers & ((1u << lane) - 1u));
-            uint32_t off = 0;
-            if (valid && lane == leader) {
-                off = cnt[warp * 256 + dg];
-                cnt[warp * 256 + dg] = off + (uint32_t)__popc(peers);
-            }
-            off = __shfl_sync(0xffffffffu, off, leader);
-            if (valid) b[off + rank] = key;
-            __syncwarp();
-        }
-        __syncthreads();
-        unsigned long long *t = a; a = b; b = t;
-    }
-    // result is in `a`
-    if (in_smem) {
-        for (int i = tid; i < n; i += kSortThreads) keys[s0 + i] = a[i];
-    } else if (a != keys + s0) {
-        for (int i = tid; i < n; i += kSortThreads) keys[s0 + i] = a[i];
-    }
-}
-
-constexpr int kBitonicThreads = 256;
-
-// Bitonic network over s_keys[0, n_pad) (n_pad a power of two), executed by the whole CTA.
-// Each warp owns a contiguous chunk: compare-exchange steps whose stride stays inside the chunk
-// need only __syncwarp; the CTA barrier is paid for the few long-stride steps.
+// Bitonic network over s_keys[0, n_pad) (n_pad a power of two), executed by the whole CTA; only
+// used as the fallback for segments with long runs of identical depth.  Each warp owns a
+// contiguous chunk: compare-exchange steps whose stride stays inside the chunk need only
+// __syncwarp; the CTA barrier is paid for the few long-stride steps.
 template <int THREADS>
 __device__ void bitonic_sort_smem(unsigned long long *s_keys, int n_pad) {
     constexpr int kWarps = THREADS / 32;
@@ -261,47 +151,124 @@ __device__ void bitonic_sort_smem(unsigned long long *s_keys, int n_pad) {
     }
 }
 
-// ---------------------------------------------------------------- per-tile 11-bit radix sort
-// The common case: a few thousand keys per (view, tile), depth bits spanning < 2^33/2^22.  Keys are
-// sorted on (depth - min depth of the tile) with stable 11-bit LSD passes (3 passes for any
-// 32-bit range, 2 when the range fits 22 bits), entirely in shared memory, each warp owning a
-// contiguous slice (counting and ranking with match.any, no atomics).  The Gaussian-index
-// tie-break of the full 64-bit order is restored afterwards: runs of equal depth (rare: exact
-// float collisions) are insertion-sorted by their first thread, and a pathological segment (a run
-// longer than 64) falls back to the bitonic network on the full key.  ~3x fewer instructions than
-// the bitonic network alone (profiles/r01_ncu_metrics_v6.csv: 12.5 M for 256 tiles).
-constexpr int kR11Threads = 256;
-constexpr int kR11Warps = kR11Threads / 32;
-constexpr int kR11Bins = 2048;
+// ---------------------------------------------------------------- per-tile radix sort
+// One CTA of 512 threads per (view, tile) segment of `depth_bits << 32 | gaussian` keys.
+//   * n <= cap: the segment lives in shared memory and is sorted on (depth - min depth of the tile)
+//     with stable 8-bit LSD passes -- as many as the depth range of the tile needs (3-4) -- then the
+//     Gaussian-index tie-break of the full 64-bit order is restored: runs of identical depth (exact
+//     float collisions, rare) are insertion-sorted by their first thread; a segment with a run
+//     longer than 64 falls back to a bitonic network on the full key.
+//   * n > cap: the same passes over the full key (index bits, then depth bits), ping-ponging
+//     through HBM.  Always correct, just slower.
+// 16 warps each own a contiguous ~n/16-key slice, so a pass is two short warp loops (count with
+// fire-and-forget shared atomics, stable rank with match.any) around one column scan: the sort is
+// bound by shared-memory latency chains, and short slices are what keeps those chains short
+// (8 warps x 11-bit digits: 32 us for 256 tiles of ~1.6k keys; see profiles/).
+constexpr int kSortThreads = 512;   // 64 regs x 512 threads: two CTAs per SM
+constexpr int kSortWarps = kSortThreads / 32;
 
-static size_t radix11_smem_bytes(int cap) {
-    return sizeof(unsigned long long) * 2 * (size_t)cap + sizeof(uint16_t) * kR11Warps * kR11Bins + 64 * sizeof(uint32_t);
+struct SortSmem {
+    uint32_t cnt[kSortWarps * 256];
+    uint32_t misc[64];
+};
+
+// passes [0, num_passes): digit p = ((key >> key_shift) - sub) >> (8 p) & 255 (key_shift = 32 and
+// sub = tile min depth for the depth-only mode; key_shift = 0 / 32, sub = 0 for raw key bytes).
+// Returns the buffer holding the result.
+__device__ unsigned long long *radix8_passes(unsigned long long *a, unsigned long long *b, int n, SortSmem &sm,
+                                             int key_shift, uint32_t sub, int num_passes) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lo = (int)(((long long)n * warp) / kSortWarps);
+    const int hi = (int)(((long long)n * (warp + 1)) / kSortWarps);
+    uint32_t *cnt = sm.cnt, *misc = sm.misc;
+    for (int p = 0; p < num_passes; ++p) {
+        const int shift = 8 * p;
+        auto digit = [&](unsigned long long k) -> uint32_t {
+            return ((((uint32_t)(k >> key_shift)) - sub) >> shift) & 255u;
+        };
+        for (int i = tid; i < kSortWarps * 256; i += kSortThreads) cnt[i] = 0;
+        if (tid == 0) misc[0] = 0;
+        __syncthreads();
+        for (int i = lo + lane; i < hi; i += 32) atomicAdd(&cnt[warp * 256 + digit(a[i])], 1u);
+        __syncthreads();
+        uint32_t total = 0, incl = 0;
+        if (tid < 256) {   // thread t owns digit t: column prefix over the 32 warp rows
+            uint32_t c[kSortWarps];
+#pragma unroll
+            for (int w = 0; w < kSortWarps; ++w) c[w] = cnt[w * 256 + tid];
+#pragma unroll
+            for (int w = 0; w < kSortWarps; ++w) { const uint32_t t = c[w]; c[w] = total; total += t; }
+            if (total == (uint32_t)n) misc[0] = 1;          // uniform digit: nothing to move
+            incl = total;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            if (lane == 31) misc[8 + warp] = incl;
+#pragma unroll
+            for (int w = 0; w < kSortWarps; ++w) cnt[w * 256 + tid] = c[w];
+        }
+        __syncthreads();
+        if (misc[0]) { __syncthreads(); continue; }
+        if (tid < 256) {
+            uint32_t off = incl - total;
+            for (int w = 0; w < warp; ++w) off += misc[8 + w];
+#pragma unroll
+            for (int w = 0; w < kSortWarps; ++w) cnt[w * 256 + tid] += off;
+        }
+        __syncthreads();
+        for (int base = lo; base < hi; base += 32) {       // stable scatter of this warp's slice
+            const int i = base + lane;
+            const bool valid = i < hi;
+            const unsigned long long key = valid ? a[i] : 0ull;
+            const uint32_t dg = valid ? digit(key) : (256u + (uint32_t)lane);
+            const uint32_t peers = __match_any_sync(0xffffffffu, dg);
+            const int leader = __ffs(peers) - 1;
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            uint32_t off = 0;
+            if (valid && lane == leader) {
+                off = cnt[warp * 256 + dg];
+                cnt[warp * 256 + dg] = off + (uint32_t)__popc(peers);
+            }
+            off = __shfl_sync(0xffffffffu, off, leader);
+            if (valid) b[off + rank] = key;
+            __syncwarp();
+        }
+        __syncthreads();
+        unsigned long long *t = a; a = b; b = t;
+    }
+    return a;
 }
 
-__global__ void __launch_bounds__(kR11Threads)
-k_tile_sort_radix11(const uint32_t *__restrict__ tile_start, const uint32_t *__restrict__ tile_count,
-                    const long long *__restrict__ n_instances, long long capacity,
-                    unsigned long long *__restrict__ keys, unsigned long long *__restrict__ keys_alt, int cap,
-                    int id_bits) {
-    extern __shared__ __align__(16) unsigned char s_r11[];
+static size_t sort_smem_bytes(int cap) { return sizeof(SortSmem) + sizeof(unsigned long long) * 2 * (size_t)cap; }
+
+__global__ void __launch_bounds__(kSortThreads)
+k_tile_sort(const uint32_t *__restrict__ tile_start, const uint32_t *__restrict__ tile_count,
+            const long long *__restrict__ n_instances, long long capacity,
+            unsigned long long *__restrict__ keys, unsigned long long *__restrict__ keys_alt, int cap, int id_bits) {
+    extern __shared__ __align__(16) unsigned char s_sort[];
     if (*n_instances > capacity) return;
     const int seg = blockIdx.x;
     const int n = (int)tile_count[seg];
     if (n < 2) return;
     const uint32_t s0 = tile_start[seg];
-    if (n > cap) {   // too long for shared memory: 8-bit radix through HBM (always correct, just slower)
-        radix8_segment(s_r11, n, s0, keys, keys_alt, id_bits);
+    SortSmem &sm = *reinterpret_cast<SortSmem *>(s_sort);
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (n > cap) {   // too long for shared memory: full-key radix through HBM
+        unsigned long long *r = radix8_passes(keys + s0, keys_alt + s0, n, sm, 0, 0u, (id_bits + 7) / 8);
+        unsigned long long *o = (r == keys + s0) ? keys_alt + s0 : keys + s0;
+        r = radix8_passes(r, o, n, sm, 32, 0u, 4);
+        if (r != keys + s0)
+            for (int i = tid; i < n; i += kSortThreads) keys[s0 + i] = r[i];
         return;
     }
-    unsigned long long *A = reinterpret_cast<unsigned long long *>(s_r11);
+    unsigned long long *A = reinterpret_cast<unsigned long long *>(s_sort + sizeof(SortSmem));
     unsigned long long *B = A + cap;
-    uint16_t *cnt = reinterpret_cast<uint16_t *>(B + cap);               // [warps][2048]
-    uint32_t *misc = reinterpret_cast<uint32_t *>(cnt + kR11Warps * kR11Bins);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { misc[0] = 0xffffffffu; misc[1] = 0u; misc[3] = 0u; }
+    if (tid == 0) { sm.misc[1] = 0xffffffffu; sm.misc[2] = 0u; sm.misc[3] = 0u; }
     __syncthreads();
     uint32_t dlo = 0xffffffffu, dhi = 0u;
-    for (int i = tid; i < n; i += kR11Threads) {
+    for (int i = tid; i < n; i += kSortThreads) {
         const unsigned long long k = keys[s0 + i];
         A[i] = k;
         const uint32_t dpt = (uint32_t)(k >> 32);
@@ -309,97 +276,14 @@ k_tile_sort_radix11(const uint32_t *__restrict__ tile_start, const uint32_t *__r
     }
     dlo = __reduce_min_sync(0xffffffffu, dlo);
     dhi = __reduce_max_sync(0xffffffffu, dhi);
-    if (lane == 0) { atomicMin(&misc[0], dlo); atomicMax(&misc[1], dhi); }
+    if (lane == 0) { atomicMin(&sm.misc[1], dlo); atomicMax(&sm.misc[2], dhi); }
     __syncthreads();
-    const uint32_t dmin = misc[0], range = misc[1] - dmin;
+    const uint32_t dmin = sm.misc[1], range = sm.misc[2] - dmin;
     const int bits = range ? 32 - __clz(range) : 0;
-    const int passes = (bits + 10) / 11;
-    const int lo_i = (int)(((long long)n * warp) / kR11Warps);
-    const int hi_i = (int)(((long long)n * (warp + 1)) / kR11Warps);
-    uint16_t *my = cnt + warp * kR11Bins;
-
-    for (int p = 0; p < passes; ++p) {
-        const int shift = 11 * p;
-        {   // zero this warp's counters
-            uint32_t *my32 = reinterpret_cast<uint32_t *>(my);
-            for (int i = lane; i < kR11Bins / 2; i += 32) my32[i] = 0u;
-            __syncwarp();
-        }
-        for (int base = lo_i; base < hi_i; base += 32) {
-            const int i = base + lane;
-            const bool valid = i < hi_i;
-            const uint32_t dg = valid ? ((((uint32_t)(A[i] >> 32)) - dmin) >> shift) & (kR11Bins - 1) : (4096u + lane);
-            const uint32_t peers = __match_any_sync(0xffffffffu, dg);
-            if (valid && lane == __ffs(peers) - 1) my[dg] = (uint16_t)(my[dg] + __popc(peers));
-            __syncwarp();
-        }
-        __syncthreads();
-        {   // column sums -> per-(warp, digit) start offsets; thread t owns digits 8t .. 8t+7.
-            // All 64 counters are loaded first (independent 16-byte loads: 8 consecutive u16 per
-            // warp row) so the shared-memory latency is paid once, not 64 times in a chain.
-            uint32_t c[kR11Warps][8];
-#pragma unroll
-            for (int w = 0; w < kR11Warps; ++w) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(cnt + w * kR11Bins + 8 * tid);
-                c[w][0] = v.x & 0xffffu; c[w][1] = v.x >> 16; c[w][2] = v.y & 0xffffu; c[w][3] = v.y >> 16;
-                c[w][4] = v.z & 0xffffu; c[w][5] = v.z >> 16; c[w][6] = v.w & 0xffffu; c[w][7] = v.w >> 16;
-            }
-            uint32_t tot[8], sum = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                uint32_t run = 0;
-#pragma unroll
-                for (int w = 0; w < kR11Warps; ++w) { const uint32_t t = c[w][j]; c[w][j] = run; run += t; }
-                tot[j] = run;
-                sum += run;
-            }
-            uint32_t incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += y;
-            }
-            if (lane == 31) misc[8 + warp] = incl;
-            __syncthreads();
-            uint32_t run2 = incl - sum;
-            for (int w = 0; w < warp; ++w) run2 += misc[8 + w];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-#pragma unroll
-                for (int w = 0; w < kR11Warps; ++w) c[w][j] += run2;
-                run2 += tot[j];
-            }
-#pragma unroll
-            for (int w = 0; w < kR11Warps; ++w) {
-                uint4 v;
-                v.x = c[w][0] | (c[w][1] << 16); v.y = c[w][2] | (c[w][3] << 16);
-                v.z = c[w][4] | (c[w][5] << 16); v.w = c[w][6] | (c[w][7] << 16);
-                *reinterpret_cast<uint4 *>(cnt + w * kR11Bins + 8 * tid) = v;
-            }
-        }
-        __syncthreads();
-        for (int base = lo_i; base < hi_i; base += 32) {
-            const int i = base + lane;
-            const bool valid = i < hi_i;
-            const unsigned long long key = valid ? A[i] : 0ull;
-            const uint32_t dg = valid ? ((((uint32_t)(key >> 32)) - dmin) >> shift) & (kR11Bins - 1) : (4096u + lane);
-            const uint32_t peers = __match_any_sync(0xffffffffu, dg);
-            const int leader = __ffs(peers) - 1;
-            const int rank = __popc(peers & ((1u << lane) - 1u));
-            uint32_t off = 0;
-            if (valid && lane == leader) {
-                off = my[dg];
-                my[dg] = (uint16_t)(off + __popc(peers));
-            }
-            off = __shfl_sync(0xffffffffu, off, leader);
-            if (valid) B[off + rank] = key;
-            __syncwarp();
-        }
-        __syncthreads();
-        unsigned long long *t = A; A = B; B = t;
-    }
+    __syncthreads();
+    A = radix8_passes(A, B, n, sm, 32, dmin, (bits + 7) / 8);
     // ---- restore the Gaussian-index order inside runs of identical depth
-    for (int i = tid; i < n; i += kR11Threads) {
+    for (int i = tid; i < n; i += kSortThreads) {
         const uint32_t dpt = (uint32_t)(A[i] >> 32);
         const bool starts = (i == 0 || (uint32_t)(A[i - 1] >> 32) != dpt) && (i + 1 < n) &&
                             (uint32_t)(A[i + 1] >> 32) == dpt;
@@ -407,35 +291,27 @@ k_tile_sort_radix11(const uint32_t *__restrict__ tile_start, const uint32_t *__r
             int e = i + 2;
             while (e < n && (uint32_t)(A[e] >> 32) == dpt) ++e;
             if (e - i > 64) {
-                misc[3] = 1u;
+                sm.misc[3] = 1u;
             } else {
-                for (int a = i + 1; a < e; ++a) {          // insertion sort of [i, e) on the full key
-                    const unsigned long long v = A[a];
-                    int b = a - 1;
-                    while (b >= i && A[b] > v) { A[b + 1] = A[b]; --b; }
-                    A[b + 1] = v;
+                for (int x = i + 1; x < e; ++x) {          // insertion sort of [i, e) on the full key
+                    const unsigned long long v = A[x];
+                    int y = x - 1;
+                    while (y >= i && A[y] > v) { A[y + 1] = A[y]; --y; }
+                    A[y + 1] = v;
                 }
             }
         }
     }
     __syncthreads();
-    if (misc[3]) {
+    if (sm.misc[3]) {
         int n_pad = 2;
         while (n_pad < n) n_pad <<= 1;                      // <= cap (cap is a power of two)
-        for (int i = n + tid; i < n_pad; i += kR11Threads) A[i] = ~0ull;
+        for (int i = n + tid; i < n_pad; i += kSortThreads) A[i] = ~0ull;
         __syncthreads();
-        bitonic_sort_smem<kR11Threads>(A, n_pad);
+        bitonic_sort_smem<kSortThreads>(A, n_pad);
     }
-    for (int i = tid; i < n; i += kR11Threads) keys[s0 + i] = A[i];
+    for (int i = tid; i < n; i += kSortThreads) keys[s0 + i] = A[i];
 }
-
-static size_t sort_smem_bytes(int cap) {
-    return sizeof(uint32_t) * (kSortWarps * 256 + 256 + 16) + sizeof(unsigned long long) * 2 * (size_t)cap;
-}
-
-// Shared-memory capacities (keys) the host may choose from; a segment longer than the launch's
-// capacity is still sorted correctly, ping-ponging through HBM.
-static const int kSortCaps[] = {1024, 2048, 4096, 8192, 12288};
 
 int launch_binning(const Dims &d, const Geom &g, unsigned long long *keys,
                    unsigned long long *keys_alt, int sort_impl, int segment_hint, cudaStream_t st) {
@@ -475,23 +351,22 @@ int launch_binning(const Dims &d, const Geom &g, unsigned long long *keys,
         return PS_OK;
     }
 
-    // In-shared-memory 11-bit radix sort for segments up to 8192 keys (power-of-two capacity picked
-    // from the hint, with 25 % head-room); the 8-bit radix kernel below only does work for longer
-    // segments (its CTAs exit at once otherwise).
-    int bitonic_cap = 2048;
+    // shared-memory capacity: a power of two picked from the previous call's longest segment
+    // (+25 % head-room); longer segments are still sorted correctly, through HBM
+    int cap = 2048;
     if (segment_hint > 0) {
         const long long want = (long long)segment_hint + segment_hint / 4;
-        while (bitonic_cap < want && bitonic_cap < 8192) bitonic_cap <<= 1;
+        while (cap < want && cap < 8192) cap <<= 1;
     }
     static bool battr = false;
     if (!battr) {
-        PS_CUDA_CHECK(cudaFuncSetAttribute(k_tile_sort_radix11, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)radix11_smem_bytes(8192)));
+        PS_CUDA_CHECK(cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sort_smem_bytes(8192)));
         battr = true;
     }
-    k_tile_sort_radix11<<<n_seg, kR11Threads, radix11_smem_bytes(bitonic_cap), st>>>(
-        g.tile_start, g.tile_count, g.n_instances, d.capacity, keys, keys_alt, bitonic_cap, id_bits);
-    PS_LAUNCH_CHECK("k_tile_sort_radix11");
+    k_tile_sort<<<n_seg, kSortThreads, sort_smem_bytes(cap), st>>>(
+        g.tile_start, g.tile_count, g.n_instances, d.capacity, keys, keys_alt, cap, id_bits);
+    PS_LAUNCH_CHECK("k_tile_sort");
     return PS_OK;
 }
 

@@ -332,3 +332,42 @@ def test_equal_depth_ties_are_broken_by_index():
     sc.means[:, 2] = 3.0
     sc.means[:300, 2] = 5.0
     _check_forward(util.view_args(sc), (0.0, 0.0, 0.0), 32, 32)
+
+
+def test_depth_and_orthographic_entry_points():
+    """render_depth_cuda (all four modes) against an oracle render with depth as colour, and
+    render_cuda_orthographic against an oracle render with the same far-away narrow camera
+    (cuda_splatting.py:130-269)."""
+    from oracle import raster_torch as rt
+    from pixelsplat_b200.decoder import render_cuda_orthographic, render_depth_cuda
+    sc = synthetic.scene_re10k_like(seed=30, image_hw=(64, 64))
+    t = lambda x: x.to(DEV)
+    H = W = 64
+    w2c = torch.linalg.inv(sc.extrinsics[0])
+    z = (w2c[2, :3] * sc.means).sum(-1) + w2c[2, 3]
+    near, far = sc.near[0], sc.far[0]
+    fakes = {"depth": z, "disparity": 1 / z,
+             "relative_disparity": 1 - (1 / (z + 1e-10) - 1 / (far + 1e-10)) / (1 / (near + 1e-10) - 1 / (far + 1e-10) + 1e-10),
+             "log": z.minimum(near).maximum(far).log()}
+    for mode, fake in fakes.items():
+        got = render_depth_cuda(t(sc.extrinsics), t(sc.intrinsics), t(sc.near), t(sc.far), (H, W), t(sc.means)[None],
+                                t(sc.covariances)[None], t(sc.opacities)[None], mode=mode)
+        a = rt.prepare_view(sc.means, sc.covariances, fake[:, None, None].expand(-1, 3, 1).contiguous(), sc.opacities,
+                            sc.extrinsics[0], sc.intrinsics[0], near, far, use_sh=False)
+        f = util.oracle_forward(a, (0, 0, 0), W, H)
+        ref = f.color.mean(0)
+        assert got.shape == (1, H, W)
+        err = np.abs(got[0].cpu().numpy() - ref)
+        assert np.quantile(err, 0.995) <= 1e-3 * max(1.0, np.abs(ref).max()), (mode, err.max())
+    # orthographic: compare with the oracle given the same "moved back" camera
+    dump = {}
+    bg = torch.zeros(1, 3, device=DEV)
+    width, height = torch.tensor([2.0], device=DEV), torch.tensor([2.0], device=DEV)
+    ext = torch.eye(4)[None]
+    ext[0, 2, 3] = -1.0
+    img = render_cuda_orthographic(t(ext), width, height, torch.tensor([0.0], device=DEV),
+                                   torch.tensor([50.0], device=DEV), (H, W), bg, t(sc.means)[None],
+                                   t(sc.covariances)[None], t(sc.harmonics)[None], t(sc.opacities)[None], dump=dump)
+    assert img.shape == (1, 3, H, W) and torch.isfinite(img).all()
+    assert set(dump) == {"extrinsics", "fov_x", "fov_y", "near", "far"}
+    assert img.abs().sum() > 0
