@@ -444,8 +444,15 @@ def main():
         dom = max(stage_ms, key=stage_ms.get)
         pk, pk_kind = peaks()
         achieved = V * ab[dom] / (stage_ms[dom] * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage's dominant kernel, from
+        # the committed `ncu --set full` capture (profiles/r01_ncu_full_v12_raw.csv), configs[1] only
+        ncu_traffic = {"composite_bwd": 28.03e6, "preprocess_bwd": 101.9e6, "tile_sort": 3.25e6}
+        traffic = ncu_traffic.get(dom) if (args.image, args.context_views, V) == (256, 2, 1) else None
         roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
-                    "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
+                    "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
+                    "note": "one 256x256 view is 0.3 waves of the machine: this kernel is issue/latency-bound "
+                            "(59-67 % issue-active, DRAM throughput ~1 %), so the HBM fraction is small by "
+                            "construction; see profiles/README.md",
                     "peak_source": f"{pk_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                     "algorithmic_bytes_per_launch": V * ab[dom], "avg_launch_ms": stage_ms[dom],
                     "pair_evals_per_s": (V * N * 256 / (stage_ms[dom] * 1e-3)

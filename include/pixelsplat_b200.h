@@ -236,6 +236,18 @@ PS_API int ps_epipolar_attention_backward(const ps_epipolar_desc *desc, const ps
                                           const float *dmass, const float *d_row, float *dq_feat,
                                           float *dq_pe, float *dbias, float *dfeatures, void *stream);
 
+/* ---- dense per-image self-attention (tcgen05, TF32 operands, FP32 accumulate) ---------------------
+ * Replaces the z = None branch of /root/reference/src/model/transformer/attention.py:54-70 as used by
+ * ImageSelfAttention (/root/reference/src/model/encoder/epipolar/image_self_attention.py:57-79):
+ *   qkv  [n_images, tokens, 3 * heads * dim_head]   output of to_qkv ("b n (qkv h d)")
+ *   out  [n_images, tokens, heads * dim_head]       softmax(q k^T * scale) v, "b n (h d)"
+ * Supported shape: tokens == 256, dim_head == 128 (pixelSplat's ViT stage at 256x256), heads <= 16;
+ * anything else returns PS_ERR_UNSUPPORTED.  debug_mode 1 writes the raw q k^T logits instead
+ * (out is then [n_images, heads, 256, 256]); used by the tests only. */
+PS_API int ps_self_attention_forward(int32_t n_images, int32_t tokens, int32_t heads, int32_t dim_head,
+                                     const float *qkv, float scale, float *out, int32_t debug_mode,
+                                     void *stream);
+
 #ifdef __cplusplus
 }
 #endif

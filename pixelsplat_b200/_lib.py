@@ -73,7 +73,8 @@ class RasterGrads(ctypes.Structure):
 EXPORTS = ("ps_version", "ps_last_error", "ps_raster_sizes_query", "ps_raster_layout_query",
            "ps_raster_forward", "ps_raster_backward", "ps_camera_setup", "ps_launch_count",
            "ps_timing_enable", "ps_timing_read", "ps_epipolar_geometry",
-           "ps_epipolar_attention_forward", "ps_epipolar_attention_backward")
+           "ps_epipolar_attention_forward", "ps_epipolar_attention_backward",
+           "ps_self_attention_forward")
 
 
 class NativeLibraryMissing(ImportError):
@@ -109,6 +110,9 @@ def _load() -> ctypes.CDLL:
     lib.ps_epipolar_attention_forward.restype = ctypes.c_int
     lib.ps_epipolar_attention_backward.argtypes = [P(EpipolarDesc), P(EpipolarInputs)] + [ctypes.c_void_p] * 10
     lib.ps_epipolar_attention_backward.restype = ctypes.c_int
+    lib.ps_self_attention_forward.argtypes = [ctypes.c_int32] * 4 + [ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p,
+                                                                      ctypes.c_int32, ctypes.c_void_p]
+    lib.ps_self_attention_forward.restype = ctypes.c_int
     for f in ("ps_raster_sizes_query", "ps_raster_layout_query", "ps_raster_forward", "ps_raster_backward"):
         getattr(lib, f).restype = ctypes.c_int
     return lib

@@ -1,0 +1,271 @@
+// Dense per-image multi-head self-attention on the 5th-generation tensor cores (tcgen05, TF32):
+//     out[img, :, head] = softmax(Q K^T * scale) V      Q, K, V: [256 tokens, 128] per (image, head)
+// for the ViT blocks of pixelSplat's ImageSelfAttention
+// (/root/reference/src/model/encoder/epipolar/image_self_attention.py:57-79 ->
+//  /root/reference/src/model/transformer/attention.py:54-70 with z = None): the only dense
+// contractions of the hot path.
+//
+// One CTA (4 warps) per (image, head, 128-query half):
+//   1. Q half [128 x 128] and K [256 x 128] are copied (fp32, read as TF32 by the MMA) into shared
+//      memory in the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices);
+//   2. one elected thread issues 16 tcgen05.mma (M=128, N=256, K=8) accumulating S = Q K^T in TMEM
+//      (256 columns), commits to an mbarrier;
+//   3. soft-max in place: thread i owns query row i = TMEM lane i; tcgen05.ld 32 columns at a time,
+//      row max, exp2, row sum, tcgen05.st the un-normalised probabilities back over S;
+//      meanwhile K's shared buffer is overwritten with V^T (d-major x tokens, same K-major layout);
+//   4. 32 tcgen05.mma (M=128, N=128, K=8) with A = P read straight from TMEM and B = V^T from
+//      shared memory accumulate O in TMEM columns 256..383;
+//   5. epilogue: tcgen05.ld O, scale by 1 / row sum, 16-byte stores to global.
+// No TMA: the tiles are tiny and L2-resident (112 CTAs x 320 KB); the copy is plain ld.global /
+// st.shared followed by a proxy fence.
+#include "ps_common.cuh"
+
+namespace ps {
+
+constexpr int kSaL = 256;        // tokens per image
+constexpr int kSaD = 128;        // head dimension
+constexpr int kSaThreads = 128;
+constexpr uint32_t kSaTmemCols = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, no swizzle: core matrix = 8 rows x 16 bytes (contiguous 128 B); 8-row groups are
+// adjacent (SBO = 128 B), 16-byte K chunks are `lbo` bytes apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+    return d;                                // base offset 0, LBO mode 0, layout type 0 (SWIZZLE_NONE)
+}
+
+// kind::tf32 instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3, M >> 4.
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+        :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar_saddr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar_saddr) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar_saddr, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done) : "r"(bar_saddr), "r"(parity) : "memory");
+    }
+}
+
+// 32 consecutive TMEM columns of this thread's lane -> registers (and back).
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    uint32_t r[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+        :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+           "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+// debug_mode: 0 = attention output; 1 = write raw S = Q K^T (first 128 columns of `out` rows unused:
+// out must then be [n_img, H, 2, 128, 256]) -- used by the tests to isolate the first MMA.
+__global__ void __launch_bounds__(kSaThreads, 1)
+k_self_attention_tc(const float *__restrict__ qkv, float *__restrict__ out, int n_heads, float scale_log2e,
+                    int debug_mode) {
+    extern __shared__ __align__(128) unsigned char s_sa[];
+    float *sQ = reinterpret_cast<float *>(s_sa);                                  // 128 x 128 fp32 = 64 KB
+    float *sK = reinterpret_cast<float *>(s_sa + 64 * 1024);                      // 256 x 128 fp32 = 128 KB (later V^T)
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_sa + 192 * 1024);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(s_sa + 192 * 1024 + 16);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int half = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
+    const int inner = n_heads * kSaD;
+    const size_t row_stride = 3 * (size_t)inner;                                   // floats per token in qkv
+    const float *q_base = qkv + ((size_t)img * kSaL + (size_t)half * 128) * row_stride + (size_t)head * kSaD;
+    const float *k_base = qkv + (size_t)img * kSaL * row_stride + inner + (size_t)head * kSaD;
+    const float *v_base = qkv + (size_t)img * kSaL * row_stride + 2 * inner + (size_t)head * kSaD;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "n"(kSaTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // ---- stage Q (128 rows) and K (256 rows): consecutive threads take consecutive rows of the same
+    // 16-byte chunk, so the shared stores are contiguous (chunk c of row r lives at c * LBO + r * 16)
+    constexpr uint32_t kLboQ = 128 * 16, kLboK = 256 * 16;                         // bytes between K chunks
+    for (int i = tid; i < 128 * 32; i += kSaThreads) {
+        const int r = i & 127, c = i >> 7;
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(q_base + (size_t)r * row_stride) + c);
+        *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sQ) + (size_t)c * kLboQ + r * 16) = v;
+    }
+    for (int i = tid; i < 256 * 32; i += kSaThreads) {
+        const int r = i & 255, c = i >> 8;
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(k_base + (size_t)r * row_stride) + c);
+        *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sK) + (size_t)c * kLboK + r * 16) = v;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                  // generic -> async proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;                                              // lane 0, column base
+    const uint32_t tmem_S = tmem, tmem_O = tmem + 256;
+
+    // ---- S = Q K^T
+    if (tid == 0) {
+        const uint32_t idesc = umma_idesc_tf32(128, 256);
+#pragma unroll 1
+        for (int k = 0; k < kSaD / 8; ++k) {
+            const uint64_t a = umma_desc(smem_u32(sQ) + k * 2 * kLboQ, kLboQ, 128);
+            const uint64_t b = umma_desc(smem_u32(sK) + k * 2 * kLboK, kLboK, 128);
+            mma_tf32_ss(tmem_S, a, b, idesc, k > 0);
+        }
+        umma_commit(smem_u32(bar));
+    }
+    mbar_wait(smem_u32(bar), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;                        // this warp's TMEM lane quarter
+    const int row = warp * 32 + lane;                                              // query row inside the half
+    if (debug_mode == 1) {
+        float *dst = out + ((((size_t)img * n_heads + head) * 2 + half) * 128 + row) * 256;
+        for (int c = 0; c < 256; c += 32) {
+            float v[32];
+            tmem_ld32(tmem_S + lane_addr + c, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dst[c + i] = v[i];
+        }
+    } else {
+        // ---- V^T into K's buffer (K is dead: the MMAs that read it have completed)
+        constexpr uint32_t kLboV = 128 * 16;
+        for (int i = tid; i < 128 * 64; i += kSaThreads) {
+            const int dd = i & 127, tg = i >> 7;                                   // row d, group of 4 tokens
+            float4 v;
+            v.x = __ldg(v_base + (size_t)(4 * tg + 0) * row_stride + dd);
+            v.y = __ldg(v_base + (size_t)(4 * tg + 1) * row_stride + dd);
+            v.z = __ldg(v_base + (size_t)(4 * tg + 2) * row_stride + dd);
+            v.w = __ldg(v_base + (size_t)(4 * tg + 3) * row_stride + dd);
+            *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sK) + (size_t)tg * kLboV + dd * 16) = v;
+        }
+        // ---- soft-max over the 256 keys of this thread's row, in place in TMEM
+        float m = -INFINITY;
+        for (int c = 0; c < 256; c += 32) {
+            float v[32];
+            tmem_ld32(tmem_S + lane_addr + c, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m = fmaxf(m, v[i]);
+        }
+        float sum = 0.0f;
+        const float mb = m * scale_log2e;
+        for (int c = 0; c < 256; c += 32) {
+            float v[32];
+            tmem_ld32(tmem_S + lane_addr + c, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                v[i] = exp2f(v[i] * scale_log2e - mb);
+                sum += v[i];
+            }
+            tmem_st32(tmem_S + lane_addr + c, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- O = P V   (A = P from TMEM, B = V^T from shared memory)
+        if (tid == 0) {
+            const uint32_t idesc = umma_idesc_tf32(128, 128);
+#pragma unroll 1
+            for (int k = 0; k < kSaL / 8; ++k) {
+                const uint64_t b = umma_desc(smem_u32(sK) + k * 2 * kLboV, kLboV, 128);
+                mma_tf32_ts(tmem_O, tmem_S + k * 8, b, idesc, k > 0);
+            }
+            umma_commit(smem_u32(bar));
+        }
+        mbar_wait(smem_u32(bar), 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const float inv = 1.0f / sum;
+        float *dst = out + ((size_t)img * kSaL + (size_t)half * 128 + row) * inner + (size_t)head * kSaD;
+        for (int c = 0; c < 128; c += 32) {
+            float v[32];
+            tmem_ld32(tmem_O + lane_addr + c, v);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4 *>(dst + c + i) = make_float4(v[i] * inv, v[i + 1] * inv, v[i + 2] * inv, v[i + 3] * inv);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(kSaTmemCols) : "memory");
+}
+
+}  // namespace ps
+
+extern "C" PS_API int ps_self_attention_forward(int32_t n_images, int32_t tokens, int32_t heads, int32_t dim_head,
+                                                const float *qkv, float scale, float *out, int32_t debug_mode,
+                                                void *stream) {
+    using namespace ps;
+    if (n_images < 1 || heads < 1 || heads > 16 || !qkv || !out) {
+        set_error("ps_self_attention_forward: bad argument");
+        return PS_ERR_INVALID_ARGUMENT;
+    }
+    if (tokens != kSaL || dim_head != kSaD) {
+        set_error("ps_self_attention_forward: only 256 tokens x 128-dim heads are supported (got %d x %d)", tokens, dim_head);
+        return PS_ERR_UNSUPPORTED;
+    }
+    if (((uintptr_t)qkv | (uintptr_t)out) & 15) { set_error("ps_self_attention_forward: pointers must be 16-byte aligned"); return PS_ERR_INVALID_ARGUMENT; }
+    const size_t smem = 192 * 1024 + 64;
+    static bool attr = false;
+    if (!attr) {
+        PS_CUDA_CHECK(cudaFuncSetAttribute(k_self_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    dim3 grid(2, heads, n_images);
+    k_self_attention_tc<<<grid, kSaThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        qkv, out, heads, scale * 1.4426950408889634f, debug_mode);
+    PS_LAUNCH_CHECK("k_self_attention_tc");
+    return PS_OK;
+}

@@ -8,12 +8,17 @@ are then never materialised -- the fused CUDA kernel gathers them from the featu
 reference's visualisers hook `transformer.layers[i][0].fn.attend`,
 encoder_visualizer_epipolar.py:53-56) the module falls back to the explicit soft-max path so the
 hook sees the [(b v r), head, 1, s*ov] attention tensor it expects.
+
+With z = None (ImageSelfAttention's ViT blocks) and the shape the kernel is written for (256 tokens,
+128-dim heads) the soft-max attention runs on the tcgen05 tensor cores
+(pixelsplat_b200/encoder/self_attention_tc.py); other shapes use torch's fp32 matmul + softmax.
 """
 from __future__ import annotations
 
 import torch
 from torch import Tensor, nn
 
+from . import self_attention_tc as _satc
 from .attention_fused import EpipolarKV, fused_epipolar_attention
 
 
@@ -45,7 +50,12 @@ class Attention(nn.Module):
                 return fused_epipolar_attention(self, x, z)
             z = z.materialize()
         if z is None:
-            q, k, v = self.to_qkv(x).chunk(3, dim=-1)
+            qkv = self.to_qkv(x)
+            hooked = len(self.attend._forward_hooks) > 0 or len(self.attend._forward_pre_hooks) > 0
+            if not hooked and _satc.supported(qkv, self.heads, self.dim_head):
+                # dense per-image self-attention on the tensor cores (csrc/self_attention_tc.cu)
+                return self.to_out(_satc.self_attention_tc(qkv, self.heads, self.scale))
+            q, k, v = qkv.chunk(3, dim=-1)
         else:
             q = self.to_q(x)
             k, v = self.to_kv(z).chunk(2, dim=-1)
