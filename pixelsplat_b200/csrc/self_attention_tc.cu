@@ -6,7 +6,7 @@
 // contractions of the hot path.
 //
 // One CTA (4 warps) per (image, head, 128-query half):
-//   1. Q half [128 x 128] and K [256 x 128] are copied (fp32, read as TF32 by the MMA) into shared
+//   1. Q half [128 x 128] and K [256 x 128] are copied (fp32 rounded to the nearest TF32) into shared
 //      memory in the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices);
 //   2. one elected thread issues 16 tcgen05.mma (M=128, N=256, K=8) accumulating S = Q K^T in TMEM
 //      (256 columns), commits to an mbarrier;
@@ -26,6 +26,15 @@ constexpr int kSaL = 256;        // tokens per image
 constexpr int kSaD = 128;        // head dimension
 constexpr int kSaThreads = 128;
 constexpr uint32_t kSaTmemCols = 512;
+
+// fp32 -> nearest TF32 (ties away), kept in an fp32 container: the tensor core ignores the low 13
+// mantissa bits, so rounding here instead of letting it truncate halves the operand error and removes its bias.
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 to_tf32(float4 v) { return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w)); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -138,12 +147,12 @@ k_self_attention_tc(const float *__restrict__ qkv, float *__restrict__ out, int 
     constexpr uint32_t kLboQ = 128 * 16, kLboK = 256 * 16;                         // bytes between K chunks
     for (int i = tid; i < 128 * 32; i += kSaThreads) {
         const int r = i & 127, c = i >> 7;
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(q_base + (size_t)r * row_stride) + c);
+        const float4 v = to_tf32(__ldg(reinterpret_cast<const float4 *>(q_base + (size_t)r * row_stride) + c));
         *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sQ) + (size_t)c * kLboQ + r * 16) = v;
     }
     for (int i = tid; i < 256 * 32; i += kSaThreads) {
         const int r = i & 255, c = i >> 8;
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(k_base + (size_t)r * row_stride) + c);
+        const float4 v = to_tf32(__ldg(reinterpret_cast<const float4 *>(k_base + (size_t)r * row_stride) + c));
         *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sK) + (size_t)c * kLboK + r * 16) = v;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                  // generic -> async proxy
@@ -152,24 +161,34 @@ k_self_attention_tc(const float *__restrict__ qkv, float *__restrict__ out, int 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;                                              // lane 0, column base
     const uint32_t tmem_S = tmem, tmem_O = tmem + 256;
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;                        // this warp's TMEM lane quarter
+    const int row = warp * 32 + lane;                                              // query row inside the half
+    if (debug_mode == 10) {                                                        // probe: alloc / dealloc only
+        if (tid == 0) out[blockIdx.x + 2 * (blockIdx.y + n_heads * blockIdx.z)] = __uint_as_float(tmem);
+    } else {
 
     // ---- S = Q K^T
     if (tid == 0) {
         const uint32_t idesc = umma_idesc_tf32(128, 256);
+        if (debug_mode != 12) {
 #pragma unroll 1
-        for (int k = 0; k < kSaD / 8; ++k) {
-            const uint64_t a = umma_desc(smem_u32(sQ) + k * 2 * kLboQ, kLboQ, 128);
-            const uint64_t b = umma_desc(smem_u32(sK) + k * 2 * kLboK, kLboK, 128);
-            mma_tf32_ss(tmem_S, a, b, idesc, k > 0);
+            for (int k = 0; k < kSaD / 8; ++k) {
+                const uint64_t a = umma_desc(smem_u32(sQ) + k * 2 * kLboQ, kLboQ, 128);
+                const uint64_t b = umma_desc(smem_u32(sK) + k * 2 * kLboK, kLboK, 128);
+                mma_tf32_ss(tmem_S, a, b, idesc, k > 0);
+            }
         }
-        umma_commit(smem_u32(bar));
+        if (debug_mode == 13)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];"
+                         :: "l"((uint64_t)__cvta_generic_to_shared(bar)) : "memory");
+        else
+            umma_commit(smem_u32(bar));
     }
     mbar_wait(smem_u32(bar), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;                        // this warp's TMEM lane quarter
-    const int row = warp * 32 + lane;                                              // query row inside the half
-    if (debug_mode == 1) {
+    if (debug_mode >= 11 && debug_mode <= 13) {                                    // probe: first MMA + commit + wait
+        if (tid == 0) out[blockIdx.x + 2 * (blockIdx.y + n_heads * blockIdx.z)] = 1.0f;
+    } else if (debug_mode == 1) {
         float *dst = out + ((((size_t)img * n_heads + head) * 2 + half) * 128 + row) * 256;
         for (int c = 0; c < 256; c += 32) {
             float v[32];
@@ -187,7 +206,7 @@ k_self_attention_tc(const float *__restrict__ qkv, float *__restrict__ out, int 
             v.y = __ldg(v_base + (size_t)(4 * tg + 1) * row_stride + dd);
             v.z = __ldg(v_base + (size_t)(4 * tg + 2) * row_stride + dd);
             v.w = __ldg(v_base + (size_t)(4 * tg + 3) * row_stride + dd);
-            *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sK) + (size_t)tg * kLboV + dd * 16) = v;
+            *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sK) + (size_t)tg * kLboV + dd * 16) = to_tf32(v);
         }
         // ---- soft-max over the 256 keys of this thread's row, in place in TMEM
         float m = -INFINITY;
@@ -204,7 +223,7 @@ k_self_attention_tc(const float *__restrict__ qkv, float *__restrict__ out, int 
             tmem_ld32(tmem_S + lane_addr + c, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                v[i] = exp2f(v[i] * scale_log2e - mb);
+                v[i] = to_tf32(exp2f(v[i] * scale_log2e - mb));   // the row sum is over what the MMA will see
                 sum += v[i];
             }
             tmem_st32(tmem_S + lane_addr + c, v);
@@ -236,6 +255,7 @@ k_self_attention_tc(const float *__restrict__ qkv, float *__restrict__ out, int 
                 *reinterpret_cast<float4 *>(dst + c + i) = make_float4(v[i] * inv, v[i + 1] * inv, v[i + 2] * inv, v[i + 3] * inv);
         }
     }
+    }   // debug_mode != 10
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
