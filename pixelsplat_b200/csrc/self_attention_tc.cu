@@ -5,17 +5,19 @@
 //  /root/reference/src/model/transformer/attention.py:54-70 with z = None): the only dense
 // contractions of the hot path.
 //
-// One CTA (4 warps) per (image, head, 128-query half):
+// One CTA (8 warps) per (image, head, 128-query half):
 //   1. Q half [128 x 128] and K [256 x 128] are copied (fp32 rounded to the nearest TF32) into shared
 //      memory in the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices);
 //   2. one elected thread issues 16 tcgen05.mma (M=128, N=256, K=8) accumulating S = Q K^T in TMEM
 //      (256 columns), commits to an mbarrier;
-//   3. soft-max in place: thread i owns query row i = TMEM lane i; tcgen05.ld 32 columns at a time,
-//      row max, exp2, row sum, tcgen05.st the un-normalised probabilities back over S;
-//      meanwhile K's shared buffer is overwritten with V^T (d-major x tokens, same K-major layout);
+//   3. warps 0-3, soft-max in place: thread i owns query row i = TMEM lane i; tcgen05.ld 32 columns
+//      at a time, row max, exp2, round to TF32, row sum, tcgen05.st the un-normalised probabilities
+//      back over S;  warps 4-7, concurrently: K's shared buffer is overwritten with V^T (d-major x
+//      tokens, same K-major layout);
 //   4. 32 tcgen05.mma (M=128, N=128, K=8) with A = P read straight from TMEM and B = V^T from
 //      shared memory accumulate O in TMEM columns 256..383;
-//   5. epilogue: tcgen05.ld O, scale by 1 / row sum, 16-byte stores to global.
+//   5. epilogue, all 8 warps (lane quarter x 64 channels each): tcgen05.ld O, scale by 1 / row sum,
+//      16-byte stores to global.
 // No TMA: the tiles are tiny and L2-resident (112 CTAs x 320 KB); the copy is plain ld.global /
 // st.shared followed by a proxy fence.
 #include "ps_common.cuh"
@@ -24,7 +26,7 @@ namespace ps {
 
 constexpr int kSaL = 256;        // tokens per image
 constexpr int kSaD = 128;        // head dimension
-constexpr int kSaThreads = 128;
+constexpr int kSaThreads = 256;      // warps 0-3: soft-max rows; warps 4-7: V^T staging; all: Q/K staging, epilogue
 constexpr uint32_t kSaTmemCols = 512;
 
 // fp32 -> nearest TF32 (ties away), kept in an fp32 container: the tensor core ignores the low 13
@@ -115,16 +117,17 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
         : "memory");
 }
 
-// debug_mode: 0 = attention output; 1 = write raw S = Q K^T (first 128 columns of `out` rows unused:
-// out must then be [n_img, H, 2, 128, 256]) -- used by the tests to isolate the first MMA.
+// debug_mode: 0 = attention output; 1 = write the raw logits S = Q K^T instead (`out` is then
+// [n_img, H, 256, 256]) -- used by the tests to isolate the first MMA stage.
 __global__ void __launch_bounds__(kSaThreads, 1)
 k_self_attention_tc(const float *__restrict__ qkv, float *__restrict__ out, int n_heads, float scale_log2e,
                     int debug_mode) {
     extern __shared__ __align__(128) unsigned char s_sa[];
-    float *sQ = reinterpret_cast<float *>(s_sa);                                  // 128 x 128 fp32 = 64 KB
-    float *sK = reinterpret_cast<float *>(s_sa + 64 * 1024);                      // 256 x 128 fp32 = 128 KB (later V^T)
+    unsigned char *sQ = s_sa;                                                      // 128 x 128 fp32 = 64 KB
+    unsigned char *sK = s_sa + 64 * 1024;                                          // 256 x 128 fp32 = 128 KB (later V^T)
     uint64_t *bar = reinterpret_cast<uint64_t *>(s_sa + 192 * 1024);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(s_sa + 192 * 1024 + 16);
+    float *s_inv = reinterpret_cast<float *>(s_sa + 192 * 1024 + 64);              // 1 / row sum, 128 rows
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int half = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
     const int inner = n_heads * kSaD;
@@ -143,17 +146,37 @@ k_self_attention_tc(const float *__restrict__ qkv, float *__restrict__ out, int 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // ---- stage Q (128 rows) and K (256 rows): consecutive threads take consecutive rows of the same
-    // 16-byte chunk, so the shared stores are contiguous (chunk c of row r lives at c * LBO + r * 16)
-    constexpr uint32_t kLboQ = 128 * 16, kLboK = 256 * 16;                         // bytes between K chunks
-    for (int i = tid; i < 128 * 32; i += kSaThreads) {
-        const int r = i & 127, c = i >> 7;
-        const float4 v = to_tf32(__ldg(reinterpret_cast<const float4 *>(q_base + (size_t)r * row_stride) + c));
-        *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sQ) + (size_t)c * kLboQ + r * 16) = v;
+    // 16-byte chunk, so the shared stores are contiguous (chunk c of row r lives at c * LBO + r * 16);
+    // eight independent 16-byte loads are in flight per thread before the first is consumed.
+    constexpr uint32_t kLboQ = 128 * 16, kLboK = 256 * 16, kLboV = 128 * 16;       // bytes between K chunks
+    constexpr int kBatch = 8;
+#pragma unroll 1
+    for (int i0 = tid; i0 < 128 * 32; i0 += kSaThreads * kBatch) {
+        float4 v[kBatch];
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            const int i = i0 + j * kSaThreads;
+            v[j] = __ldg(reinterpret_cast<const float4 *>(q_base + (size_t)(i & 127) * row_stride) + (i >> 7));
+        }
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            const int i = i0 + j * kSaThreads;
+            *reinterpret_cast<float4 *>(sQ + (size_t)(i >> 7) * kLboQ + (i & 127) * 16) = to_tf32(v[j]);
+        }
     }
-    for (int i = tid; i < 256 * 32; i += kSaThreads) {
-        const int r = i & 255, c = i >> 8;
-        const float4 v = to_tf32(__ldg(reinterpret_cast<const float4 *>(k_base + (size_t)r * row_stride) + c));
-        *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sK) + (size_t)c * kLboK + r * 16) = v;
+#pragma unroll 1
+    for (int i0 = tid; i0 < 256 * 32; i0 += kSaThreads * kBatch) {
+        float4 v[kBatch];
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            const int i = i0 + j * kSaThreads;
+            v[j] = __ldg(reinterpret_cast<const float4 *>(k_base + (size_t)(i & 255) * row_stride) + (i >> 8));
+        }
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            const int i = i0 + j * kSaThreads;
+            *reinterpret_cast<float4 *>(sK + (size_t)(i >> 8) * kLboK + (i & 255) * 16) = to_tf32(v[j]);
+        }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                  // generic -> async proxy
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -161,74 +184,79 @@ k_self_attention_tc(const float *__restrict__ qkv, float *__restrict__ out, int 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;                                              // lane 0, column base
     const uint32_t tmem_S = tmem, tmem_O = tmem + 256;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;                        // this warp's TMEM lane quarter
-    const int row = warp * 32 + lane;                                              // query row inside the half
-    if (debug_mode == 10) {                                                        // probe: alloc / dealloc only
-        if (tid == 0) out[blockIdx.x + 2 * (blockIdx.y + n_heads * blockIdx.z)] = __uint_as_float(tmem);
-    } else {
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;                  // this warp's TMEM lane quarter
+    const int row = (warp & 3) * 32 + lane;                                        // query row inside the half
 
     // ---- S = Q K^T
     if (tid == 0) {
         const uint32_t idesc = umma_idesc_tf32(128, 256);
-        if (debug_mode != 12) {
 #pragma unroll 1
-            for (int k = 0; k < kSaD / 8; ++k) {
-                const uint64_t a = umma_desc(smem_u32(sQ) + k * 2 * kLboQ, kLboQ, 128);
-                const uint64_t b = umma_desc(smem_u32(sK) + k * 2 * kLboK, kLboK, 128);
-                mma_tf32_ss(tmem_S, a, b, idesc, k > 0);
-            }
+        for (int k = 0; k < kSaD / 8; ++k) {
+            const uint64_t a = umma_desc(smem_u32(sQ) + k * 2 * kLboQ, kLboQ, 128);
+            const uint64_t b = umma_desc(smem_u32(sK) + k * 2 * kLboK, kLboK, 128);
+            mma_tf32_ss(tmem_S, a, b, idesc, k > 0);
         }
-        if (debug_mode == 13)
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];"
-                         :: "l"((uint64_t)__cvta_generic_to_shared(bar)) : "memory");
-        else
-            umma_commit(smem_u32(bar));
+        umma_commit(smem_u32(bar));
     }
     mbar_wait(smem_u32(bar), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (debug_mode >= 11 && debug_mode <= 13) {                                    // probe: first MMA + commit + wait
-        if (tid == 0) out[blockIdx.x + 2 * (blockIdx.y + n_heads * blockIdx.z)] = 1.0f;
-    } else if (debug_mode == 1) {
-        float *dst = out + ((((size_t)img * n_heads + head) * 2 + half) * 128 + row) * 256;
-        for (int c = 0; c < 256; c += 32) {
-            float v[32];
-            tmem_ld32(tmem_S + lane_addr + c, v);
+    if (debug_mode == 1) {
+        if (warp < 4) {
+            float *dst = out + ((((size_t)img * n_heads + head) * 2 + half) * 128 + row) * 256;
+            for (int c = 0; c < 256; c += 32) {
+                float v[32];
+                tmem_ld32(tmem_S + lane_addr + c, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) dst[c + i] = v[i];
+                for (int i = 0; i < 32; ++i) dst[c + i] = v[i];
+            }
         }
     } else {
-        // ---- V^T into K's buffer (K is dead: the MMAs that read it have completed)
-        constexpr uint32_t kLboV = 128 * 16;
-        for (int i = tid; i < 128 * 64; i += kSaThreads) {
-            const int dd = i & 127, tg = i >> 7;                                   // row d, group of 4 tokens
-            float4 v;
-            v.x = __ldg(v_base + (size_t)(4 * tg + 0) * row_stride + dd);
-            v.y = __ldg(v_base + (size_t)(4 * tg + 1) * row_stride + dd);
-            v.z = __ldg(v_base + (size_t)(4 * tg + 2) * row_stride + dd);
-            v.w = __ldg(v_base + (size_t)(4 * tg + 3) * row_stride + dd);
-            *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sK) + (size_t)tg * kLboV + dd * 16) = to_tf32(v);
-        }
-        // ---- soft-max over the 256 keys of this thread's row, in place in TMEM
-        float m = -INFINITY;
-        for (int c = 0; c < 256; c += 32) {
-            float v[32];
-            tmem_ld32(tmem_S + lane_addr + c, v);
+        if (warp >= 4) {
+            // ---- warps 4-7: V^T into K's buffer (K is dead: the MMAs that read it have completed);
+            // one 16-byte chunk = 4 consecutive tokens of one channel, 16 scalar loads in flight
+            const int t4 = tid - 128;
+#pragma unroll 1
+            for (int i0 = t4; i0 < 128 * 64; i0 += 128 * 4) {
+                float4 v[4];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m = fmaxf(m, v[i]);
-        }
-        float sum = 0.0f;
-        const float mb = m * scale_log2e;
-        for (int c = 0; c < 256; c += 32) {
-            float v[32];
-            tmem_ld32(tmem_S + lane_addr + c, v);
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + j * 128;
+                    const float *src = v_base + (size_t)(4 * (i >> 7)) * row_stride + (i & 127);
+                    v[j].x = __ldg(src);
+                    v[j].y = __ldg(src + row_stride);
+                    v[j].z = __ldg(src + 2 * row_stride);
+                    v[j].w = __ldg(src + 3 * row_stride);
+                }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                v[i] = to_tf32(exp2f(v[i] * scale_log2e - mb));   // the row sum is over what the MMA will see
-                sum += v[i];
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + j * 128;
+                    *reinterpret_cast<float4 *>(sK + (size_t)(i >> 7) * kLboV + (i & 127) * 16) = to_tf32(v[j]);
+                }
             }
-            tmem_st32(tmem_S + lane_addr + c, v);
+        } else {
+            // ---- warps 0-3: soft-max over the 256 keys of this thread's row, in place in TMEM
+            float m = -INFINITY;
+            for (int c = 0; c < 256; c += 32) {
+                float v[32];
+                tmem_ld32(tmem_S + lane_addr + c, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) m = fmaxf(m, v[i]);
+            }
+            float sum = 0.0f;
+            const float mb = m * scale_log2e;
+            for (int c = 0; c < 256; c += 32) {
+                float v[32];
+                tmem_ld32(tmem_S + lane_addr + c, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    v[i] = to_tf32(exp2f(v[i] * scale_log2e - mb));   // the row sum is over what the MMA will see
+                    sum += v[i];
+                }
+                tmem_st32(tmem_S + lane_addr + c, v);
+            }
+            s_inv[row] = 1.0f / sum;
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -245,17 +273,18 @@ k_self_attention_tc(const float *__restrict__ qkv, float *__restrict__ out, int 
         }
         mbar_wait(smem_u32(bar), 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const float inv = 1.0f / sum;
-        float *dst = out + ((size_t)img * kSaL + (size_t)half * 128 + row) * inner + (size_t)head * kSaD;
-        for (int c = 0; c < 128; c += 32) {
+        // ---- epilogue: every warp takes its lane quarter x 64 of the 128 output channels
+        const float inv = s_inv[row];
+        const int c0 = (warp >> 2) * 64;
+        float *dst = out + ((size_t)img * kSaL + (size_t)half * 128 + row) * inner + (size_t)head * kSaD + c0;
+        for (int c = 0; c < 64; c += 32) {
             float v[32];
-            tmem_ld32(tmem_O + lane_addr + c, v);
+            tmem_ld32(tmem_O + lane_addr + c0 + c, v);
 #pragma unroll
             for (int i = 0; i < 32; i += 4)
                 *reinterpret_cast<float4 *>(dst + c + i) = make_float4(v[i] * inv, v[i + 1] * inv, v[i + 2] * inv, v[i + 3] * inv);
         }
     }
-    }   // debug_mode != 10
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
@@ -277,7 +306,7 @@ extern "C" PS_API int ps_self_attention_forward(int32_t n_images, int32_t tokens
         return PS_ERR_UNSUPPORTED;
     }
     if (((uintptr_t)qkv | (uintptr_t)out) & 15) { set_error("ps_self_attention_forward: pointers must be 16-byte aligned"); return PS_ERR_INVALID_ARGUMENT; }
-    const size_t smem = 192 * 1024 + 64;
+    const size_t smem = 192 * 1024 + 64 + 128 * sizeof(float);
     static bool attr = false;
     if (!attr) {
         PS_CUDA_CHECK(cudaFuncSetAttribute(k_self_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
