@@ -248,6 +248,47 @@ PS_API int ps_self_attention_forward(int32_t n_images, int32_t tokens, int32_t h
                                      const float *qkv, float scale, float *out, int32_t debug_mode,
                                      void *stream);
 
+/* ---- fused GaussianAdapter ----------------------------------------------
+ * Replaces /root/reference/src/model/encoder/common/gaussian_adapter.py:48-95 (+ gaussians.py:8-44):
+ * per-ray raw network outputs -> world-space Gaussians.  One camera = one (batch, view) pair; every
+ * ray carries n_samples Gaussians that share its raw features and differ in depth.
+ *   means [n_views, n_rays, n_samples, 3]      covariances [.., 3, 3]      harmonics [.., 3, sh_coeffs]
+ *   scales [.., 3] (optional, may be NULL)      rotations [n_views, n_rays, 4] xyzw (optional)
+ * Opacities pass through the reference's adapter unchanged and are not part of this call. */
+typedef struct ps_adapter_desc {
+    int32_t n_views;      /* b * v cameras */
+    int32_t n_rays;       /* rays x surfaces per camera */
+    int32_t n_samples;    /* Gaussians per ray (1..8) */
+    int32_t sh_coeffs;    /* (degree + 1)^2, degree <= 4 */
+    int32_t image_h, image_w;
+    float scale_min, scale_max; /* GaussianAdapterCfg.gaussian_scale_min / max */
+    float eps;            /* 1e-8 in the reference */
+    int32_t reserved;
+} ps_adapter_desc;
+
+typedef struct ps_adapter_inputs {
+    const float *extrinsics;   /* [n_views, 4, 4] camera-to-world */
+    const float *intrinsics;   /* [n_views, 3, 3] normalised */
+    const float *sh_rotation;  /* [n_views, sh_coeffs, sh_coeffs] block-diagonal D(c2w): c' = D c */
+    const float *sh_mask;      /* [sh_coeffs] */
+    const float *coordinates;  /* [n_views, n_rays, 2] */
+    const float *depths;       /* [n_views, n_rays, n_samples] */
+    const float *raw;          /* [n_views, n_rays, 7 + 3 sh_coeffs]: scale logits 3, quaternion xyzw 4, sh [3, sh_coeffs] */
+} ps_adapter_inputs;
+
+PS_API int ps_gaussian_adapter_forward(const ps_adapter_desc *desc, const ps_adapter_inputs *in, float *means,
+                                       float *covariances, float *harmonics, float *scales, float *rotations,
+                                       void *stream);
+
+/* d_scales / d_rotations may be NULL (no gradient reached those outputs).  Outputs: d_coordinates
+ * [n_views, n_rays, 2], d_depths [n_views, n_rays, n_samples], d_raw [n_views, n_rays, 7 + 3 sh_coeffs]
+ * (all fully written, no zero-initialisation needed). */
+PS_API int ps_gaussian_adapter_backward(const ps_adapter_desc *desc, const ps_adapter_inputs *in,
+                                        const float *d_means, const float *d_covariances,
+                                        const float *d_harmonics, const float *d_scales,
+                                        const float *d_rotations, float *d_coordinates, float *d_depths,
+                                        float *d_raw, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

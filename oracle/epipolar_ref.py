@@ -61,3 +61,17 @@ def load(num_context_views: int = 2):
         depth_to_relative_disparity=conversions.depth_to_relative_disparity,
     )
     return ns
+
+
+def load_adapter():
+    """The reference's GaussianAdapter / DepthPredictorMonocular.  The adapter
+    module imports e3nn through src/misc/sh_rotation.py; oracle/_stubs/e3nn makes that import succeed
+    and the returned namespace exposes the module object so the caller can replace `rotate_sh`
+    (golden outputs are generated with the rotation factored out -- see make_adapter_golden.py)."""
+    load(2)
+    from src.model.encoder.common import gaussian_adapter
+    from src.model.encoder.epipolar import depth_predictor_monocular
+    return types.SimpleNamespace(
+        module=gaussian_adapter, GaussianAdapter=gaussian_adapter.GaussianAdapter,
+        GaussianAdapterCfg=gaussian_adapter.GaussianAdapterCfg,
+        DepthPredictorMonocular=depth_predictor_monocular.DepthPredictorMonocular)

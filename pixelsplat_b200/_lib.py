@@ -65,6 +65,18 @@ class EpipolarInputs(ctypes.Structure):
         "features", "segments", "valid", "rel_disparity", "q_feat", "q_pe", "bias")]
 
 
+class AdapterDesc(ctypes.Structure):
+    _fields_ = [("n_views", ctypes.c_int32), ("n_rays", ctypes.c_int32), ("n_samples", ctypes.c_int32),
+                ("sh_coeffs", ctypes.c_int32), ("image_h", ctypes.c_int32), ("image_w", ctypes.c_int32),
+                ("scale_min", ctypes.c_float), ("scale_max", ctypes.c_float), ("eps", ctypes.c_float),
+                ("reserved", ctypes.c_int32)]
+
+
+class AdapterInputs(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        "extrinsics", "intrinsics", "sh_rotation", "sh_mask", "coordinates", "depths", "raw")]
+
+
 class RasterGrads(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
         "d_means", "d_cov", "d_opacities", "d_sh", "d_means2d")]
@@ -74,7 +86,7 @@ EXPORTS = ("ps_version", "ps_last_error", "ps_raster_sizes_query", "ps_raster_la
            "ps_raster_forward", "ps_raster_backward", "ps_camera_setup", "ps_launch_count",
            "ps_timing_enable", "ps_timing_read", "ps_epipolar_geometry",
            "ps_epipolar_attention_forward", "ps_epipolar_attention_backward",
-           "ps_self_attention_forward")
+           "ps_self_attention_forward", "ps_gaussian_adapter_forward", "ps_gaussian_adapter_backward")
 
 
 class NativeLibraryMissing(ImportError):
@@ -113,6 +125,10 @@ def _load() -> ctypes.CDLL:
     lib.ps_self_attention_forward.argtypes = [ctypes.c_int32] * 4 + [ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p,
                                                                       ctypes.c_int32, ctypes.c_void_p]
     lib.ps_self_attention_forward.restype = ctypes.c_int
+    lib.ps_gaussian_adapter_forward.argtypes = [P(AdapterDesc), P(AdapterInputs)] + [ctypes.c_void_p] * 6
+    lib.ps_gaussian_adapter_forward.restype = ctypes.c_int
+    lib.ps_gaussian_adapter_backward.argtypes = [P(AdapterDesc), P(AdapterInputs)] + [ctypes.c_void_p] * 9
+    lib.ps_gaussian_adapter_backward.restype = ctypes.c_int
     for f in ("ps_raster_sizes_query", "ps_raster_layout_query", "ps_raster_forward", "ps_raster_backward"):
         getattr(lib, f).restype = ctypes.c_int
     return lib

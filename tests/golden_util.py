@@ -51,15 +51,41 @@ def camera_rig(b: int, v: int, case: str = "generic"):
             s = 0.37 * bi + 0.91 * vi
             if case == "generic":
                 ext[bi, vi, :3, :3] = rotation(0.03 * math.sin(s), 0.08 * math.cos(2 * s) * vi, 0.02 * math.sin(3 * s))
-                ext[bi, vi, :3, 3] = torch.tensor([1.0 * vi / max(v - 1, 1), 0.05 * math.sin(s), 0.04 * math.cos(s)])
+                ext[bi, vi, :3, 3] = torch.tensor([1.0 * vi / max(v - 1, 1), 0.05 * math.sin(s), 0.04 * math.cos(s)],
+                                                   dtype=torch.float64)
             elif case == "parallel":
-                ext[bi, vi, :3, 3] = torch.tensor([0.0 if vi < 2 else 0.5, 0.0, 0.0])
+                ext[bi, vi, :3, 3] = torch.tensor([0.0 if vi < 2 else 0.5, 0.0, 0.0], dtype=torch.float64)
             elif case == "diverging":
                 ext[bi, vi, :3, :3] = rotation(0.0, (1.2 if vi % 2 else -1.2), 0.0)
-                ext[bi, vi, :3, 3] = torch.tensor([0.3 * vi, 0.0, 0.0])
+                ext[bi, vi, :3, 3] = torch.tensor([0.3 * vi, 0.0, 0.0], dtype=torch.float64)
             f = 0.88 + 0.03 * math.sin(1.7 * s)
             K[bi, vi, 0, 0], K[bi, vi, 1, 1] = f, f * 1.02
             K[bi, vi, 0, 2], K[bi, vi, 1, 2] = 0.5 + 0.01 * math.cos(s), 0.5 - 0.01 * math.sin(s)
     near = torch.full((b, v), 0.293, dtype=torch.float64) * (1 + 0.1 * torch.arange(v, dtype=torch.float64))
     far = torch.full((b, v), 450.6, dtype=torch.float64)
     return ext, K, near, far
+
+
+def adapter_case(b: int = 2, v: int = 2, r: int = 40, srf: int = 1, spp: int = 3, d_sh: int = 25, case: str = "generic"):
+    """Inputs of GaussianAdapter.forward in EncoderEpipolar's call shape (float64): extrinsics
+    [b,v,1,1,1,4,4], intrinsics [b,v,1,1,1,3,3], coordinates [b,v,r,srf,1,2] in (0,1), depths and
+    opacities [b,v,r,srf,spp], raw [b,v,r,srf,1,7+3 d_sh], plus loss weights for every output."""
+    ext, K, near, far = camera_rig(b, v, case)
+    lead = (b, v, r, srf, spp)
+    coords = torch.sigmoid(seeded_like("adapter.coords", (b, v, r, srf, 1, 2)))
+    u = torch.sigmoid(seeded_like("adapter.depth", lead))
+    depths = 1.0 / ((1 - u) * (1 / near - 1 / far)[:, :, None, None, None] + (1 / far)[:, :, None, None, None])
+    opac = torch.sigmoid(seeded_like("adapter.opacity", lead)) / spp
+    raw = seeded_like("adapter.raw", (b, v, r, srf, 1, 7 + 3 * d_sh))
+    weights = {k: seeded_like("adapter.w." + k, shape) for k, shape in dict(
+        means=(*lead, 3), covariances=(*lead, 3, 3), harmonics=(*lead, 3, d_sh), scales=(*lead, 3),
+        rotations=(*lead, 4), opacities=lead).items()}
+    return dict(extrinsics=ext[:, :, None, None, None], intrinsics=K[:, :, None, None, None], coordinates=coords,
+                depths=depths, opacities=opac, raw=raw, near=near, far=far, weights=weights)
+
+
+def adapter_loss(g, weights) -> torch.Tensor:
+    """A scalar that touches every output of the adapter (covariances weighted up: they are ~1e-4)."""
+    return ((g.means * weights["means"]).sum() + 1e3 * (g.covariances * weights["covariances"]).sum()
+            + (g.harmonics * weights["harmonics"]).sum() + 10.0 * (g.scales * weights["scales"]).sum()
+            + (g.rotations * weights["rotations"]).sum() + (g.opacities * weights["opacities"]).sum())

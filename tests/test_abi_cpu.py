@@ -35,17 +35,21 @@ def test_ctypes_structs_match_the_header(tmp_path):
     from pixelsplat_b200 import _lib
     probe = tmp_path / "probe.c"
     probe.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pixelsplat_b200.h"\n'
-                     "int main(void){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu\\n\","
+                     "int main(void){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n\","
                      "sizeof(ps_raster_desc),offsetof(ps_raster_desc,instance_capacity),"
                      "sizeof(ps_raster_inputs),sizeof(ps_raster_state),sizeof(ps_raster_sizes),"
-                     "sizeof(ps_raster_layout),sizeof(ps_raster_grads),offsetof(ps_raster_desc,sort_impl));return 0;}\n")
+                     "sizeof(ps_raster_layout),sizeof(ps_raster_grads),offsetof(ps_raster_desc,sort_impl),"
+                     "sizeof(ps_epipolar_desc),sizeof(ps_epipolar_inputs),sizeof(ps_adapter_desc),"
+                     "offsetof(ps_adapter_desc,scale_min),sizeof(ps_adapter_inputs));return 0;}\n")
     exe = tmp_path / "probe"
     subprocess.run(["gcc", "-I", str(HEADER.parent), str(probe), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [ctypes.sizeof(_lib.RasterDesc), _lib.RasterDesc.instance_capacity.offset,
             ctypes.sizeof(_lib.RasterInputs), ctypes.sizeof(_lib.RasterState),
             ctypes.sizeof(_lib.RasterSizes), ctypes.sizeof(_lib.RasterLayout),
-            ctypes.sizeof(_lib.RasterGrads), _lib.RasterDesc.sort_impl.offset]
+            ctypes.sizeof(_lib.RasterGrads), _lib.RasterDesc.sort_impl.offset,
+            ctypes.sizeof(_lib.EpipolarDesc), ctypes.sizeof(_lib.EpipolarInputs), ctypes.sizeof(_lib.AdapterDesc),
+            _lib.AdapterDesc.scale_min.offset, ctypes.sizeof(_lib.AdapterInputs)]
     assert got == want
 
 

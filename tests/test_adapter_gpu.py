@@ -1,0 +1,141 @@
+"""GPU parity tests of the fused GaussianAdapter (csrc/gaussian_adapter.cu).
+
+Against the REFERENCE module's golden outputs (tests/golden/adapter_v1.npz; float64 and float32 runs
+of /root/reference's GaussianAdapter with the e3nn-based `rotate_sh` factored out -- e3nn is absent
+offline, so the SH rotation is compared against this package's own torch path only, and against its
+defining properties in tests/test_adapter_cpu.py).
+
+Stated tolerance: our fp32 error against the float64 reference must stay within 4x the reference's
+OWN fp32-vs-float64 error (both are single-precision evaluations of the same formulas in different
+operation orders) and below 2e-5 relative (max-norm) for every output and every gradient.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from tests import golden_util as gu
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLD = np.load(Path(__file__).resolve().parent / "golden" / "adapter_v1.npz")
+IMAGE_SHAPE = (48, 64)
+OUT_KEYS = ("means", "covariances", "scales", "opacities", "harmonics")
+LEAVES = ("coordinates", "depths", "opacities", "raw")
+
+
+def _adapter(degree=4):
+    from pixelsplat_b200.encoder.gaussian_adapter import GaussianAdapter, GaussianAdapterCfg
+    return GaussianAdapter(GaussianAdapterCfg(0.5, 15.0, degree)).to(DEV)
+
+
+def _run(ad, c, fused=True, rotate=True):
+    t = {k: v.to(DEV, torch.float32) for k, v in c.items() if torch.is_tensor(v)}
+    w = {k: v.to(DEV, torch.float32) for k, v in c["weights"].items()}
+    leaves = {k: t[k].clone().requires_grad_(True) for k in LEAVES}
+    args = (t["extrinsics"], t["intrinsics"], leaves["coordinates"], leaves["depths"], leaves["opacities"], leaves["raw"],
+            IMAGE_SHAPE)
+    g = ad(*args) if fused else ad.forward_explicit(*args, rotate=rotate)
+    gu.adapter_loss(g, w).backward()
+    return g, {k: v.grad for k, v in leaves.items()}
+
+
+@pytest.mark.parametrize("case", ["generic", "diverging"])
+def test_fused_adapter_matches_reference(case, monkeypatch):
+    from pixelsplat_b200 import _lib
+    from pixelsplat_b200.encoder import gaussian_adapter as ga
+    # factor the SH rotation out exactly as the golden generator did
+    monkeypatch.setattr(ga, "sh_rotation_matrices",
+                        lambda R, degree: torch.eye((degree + 1) ** 2, device=R.device).expand(*R.shape[:-2], -1, -1))
+    before = _lib.lib.ps_launch_count()
+    g, grads = _run(_adapter(), gu.adapter_case(case=case))
+    assert _lib.lib.ps_launch_count() == before + 2          # one forward, one backward kernel
+    for k in OUT_KEYS + ("rotations",):
+        ours = getattr(g, k).detach().cpu().numpy()
+        if k == "rotations":
+            assert ours.shape[-2] == 3 and np.array_equal(ours[..., :1, :], ours[..., 1:2, :])   # broadcast over spp
+            ours = ours[..., :1, :]
+        ref64, ref32 = GOLD[f"{case}_f64_{k}"], GOLD[f"{case}_f32_{k}"]
+        err, own = rel_err(ours, ref64), rel_err(ref32, ref64)
+        assert err < max(4 * own, 1e-6) and err < 2e-5, (k, err, own)
+    for k in LEAVES:
+        ref64, ref32 = GOLD[f"{case}_f64_d_{k}"], GOLD[f"{case}_f32_d_{k}"]
+        err, own = rel_err(grads[k].cpu().numpy(), ref64), rel_err(ref32, ref64)
+        assert err < max(4 * own, 1e-6) and err < 2e-5, ("d_" + k, err, own)
+
+
+@pytest.mark.parametrize("degree,r,spp", [(4, 40, 3), (4, 97, 1), (2, 33, 2), (0, 5, 3), (3, 64, 8), (1, 31, 3)])
+def test_fused_equals_explicit_path_with_rotation(degree, r, spp):
+    """Real camera rotations (SH rotation active), ragged ray counts, every SH degree, 1..8 samples."""
+    d_sh = (degree + 1) ** 2
+    c = gu.adapter_case(b=1, v=3, r=r, srf=1, spp=spp, d_sh=d_sh, case="diverging")
+    ad = _adapter(degree)
+    g_f, grads_f = _run(ad, c, fused=True)
+    g_e, grads_e = _run(ad, c, fused=False)
+    for k in OUT_KEYS + ("rotations",):
+        a, b = getattr(g_f, k).detach().cpu().numpy(), getattr(g_e, k).detach().cpu().numpy()
+        assert a.shape == b.shape and rel_err(a, b) < 5e-6, k
+    for k in LEAVES:
+        assert rel_err(grads_f[k].cpu().numpy(), grads_e[k].cpu().numpy()) < 2e-5, k
+
+
+def test_two_surfaces_and_unusual_broadcast_fall_back():
+    from pixelsplat_b200 import _lib
+    ad = _adapter()
+    c = gu.adapter_case(b=1, v=2, r=20, srf=2, spp=3)
+    g, _ = _run(ad, c)                                        # srf = 2 is still the fused path
+    assert g.means.shape == (1, 2, 20, 2, 3, 3)
+    ge, _ = _run(ad, c, fused=False)
+    assert rel_err(g.covariances.detach().cpu().numpy(), ge.covariances.detach().cpu().numpy()) < 5e-6
+    # per-sample raw features (not constant over spp): explicit path, no kernel launch
+    t = {k: v.to(DEV, torch.float32) for k, v in c.items() if torch.is_tensor(v)}
+    before = _lib.lib.ps_launch_count()
+    g2 = ad(t["extrinsics"], t["intrinsics"], t["coordinates"], t["depths"], t["opacities"],
+            t["raw"].expand(-1, -1, -1, -1, 3, -1).contiguous(), IMAGE_SHAPE)
+    assert _lib.lib.ps_launch_count() == before and g2.means.shape == g.means.shape
+    with pytest.raises(ValueError, match="no CPU path"):
+        ad.cpu()(*[c[k].float() for k in ("extrinsics", "intrinsics", "coordinates", "depths", "opacities", "raw")], IMAGE_SHAPE)
+
+
+def test_encoder_tail_produces_decoder_ready_gaussians():
+    """features -> Gaussians -> render -> backward, at 32x32: the encoder tail feeds the rasterizer."""
+    from pixelsplat_b200.decoder import DecoderSplattingCUDA, DecoderSplattingCUDACfg
+    from pixelsplat_b200.encoder.encoder_tail import EncoderEpipolarTail, EncoderTailCfg
+    torch.manual_seed(0)
+    b, v, h, w = 1, 2, 32, 32
+    tail = EncoderEpipolarTail(EncoderTailCfg()).to(DEV)
+    ext, K, near, far = [t.to(DEV, torch.float32) for t in gu.camera_rig(b, v)]
+    ctx = dict(image=torch.rand(b, v, 3, h, w, device=DEV), extrinsics=ext, intrinsics=K, near=near, far=far)
+    feats = torch.randn(b, v, 128, h, w, device=DEV, requires_grad=True)
+    dump = {}
+    gs = tail(feats, ctx, global_step=0, visualization_dump=dump)
+    n = v * h * w * 3
+    assert gs.means.shape == (b, n, 3) and gs.covariances.shape == (b, n, 3, 3)
+    assert gs.harmonics.shape == (b, n, 3, 25) and gs.opacities.shape == (b, n)
+    assert dump["depth"].shape == (b, v, h, w, 1, 3) and dump["scales"].shape == (b, n, 3)
+    dec = DecoderSplattingCUDA(DecoderSplattingCUDACfg("splatting_cuda"),
+                               type("D", (), {"background_color": [0.0, 0.0, 0.0]})()).to(DEV)
+    out = dec(gs, ext, K, near, far, (h, w))
+    out.color.square().mean().backward()
+    assert torch.isfinite(feats.grad).all() and feats.grad.abs().max() > 0
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in tail.parameters())
+    keys = set(tail.state_dict())
+    assert {"depth_predictor.projection.1.weight", "to_gaussians.1.weight", "high_resolution_skip.0.weight"} <= keys
+    det = tail(feats, ctx, deterministic=True)                # 1 Gaussian per pixel
+    assert det.means.shape == (b, v * h * w, 3)
+
+
+def test_abi_rejects_bad_descriptors():
+    import ctypes
+    from pixelsplat_b200 import _lib
+    buf = torch.zeros(4096, device=DEV)
+    ins = _lib.AdapterInputs(*[buf.data_ptr()] * 7)
+    p = ctypes.c_void_p(buf.data_ptr())
+    bad_sh = _lib.AdapterDesc(1, 4, 3, 7, 8, 8, 0.5, 15.0, 1e-8, 0)
+    assert _lib.lib.ps_gaussian_adapter_forward(ctypes.byref(bad_sh), ctypes.byref(ins), p, p, p, None, None, None) == 3
+    bad_n = _lib.AdapterDesc(1, 4, 9, 25, 8, 8, 0.5, 15.0, 1e-8, 0)
+    assert _lib.lib.ps_gaussian_adapter_forward(ctypes.byref(bad_n), ctypes.byref(ins), p, p, p, None, None, None) == 1
+    ok = _lib.AdapterDesc(1, 4, 3, 25, 8, 8, 0.5, 15.0, 1e-8, 0)
+    assert _lib.lib.ps_gaussian_adapter_backward(ctypes.byref(ok), ctypes.byref(ins), p, p, None, None, None, p, p, p, None) == 1
