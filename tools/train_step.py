@@ -4,9 +4,8 @@ optimisation step, data-parallel over GPUs.
 
     features [B, 2, 128, 256, 256]  (synthetic stand-in for the out-of-scope DINO/ResNet backbone)
       -> EpipolarTransformer                       (hot path, rows a8-a15; trainable)
-      -> per-pixel Gaussian head                   (minimal stand-in for the depth predictor +
-                                                    GaussianAdapter, SURVEY 8f-1: Linear(128, 3*84) and
-                                                    the adapter's closed-form mapping, in torch)
+      -> EncoderEpipolarTail                       (row f-1: high-res skip, depth predictor, to_gaussians,
+                                                    fused GaussianAdapter kernel; trainable)
       -> DecoderSplattingCUDA, 4 target views/scene (hot path, rows a1-a7; V cameras share Gaussians)
       -> MSE -> backward -> bucketed NCCL gradient all-reduce -> clip 0.5 -> Adam
 
@@ -30,51 +29,6 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 
 
-class GaussianHead(nn.Module):
-    """features [b, v, c, h, w] -> pixelSplat `Gaussians` (3 per pixel), with the adapter's
-    parameterisation (gaussian_adapter.py:60-95): depth in relative disparity, scale =
-    (0.5 + 14.5 sigmoid) * depth * 0.1 * (px + py), unit quaternion -> R S S^T R^T, SH * sh_mask."""
-
-    def __init__(self, c: int, gpp: int = 3, sh_degree: int = 4):
-        super().__init__()
-        self.gpp, self.d_sh = gpp, (sh_degree + 1) ** 2
-        self.proj = nn.Linear(c, gpp * (2 + 3 + 4 + 3 * self.d_sh))
-        mask = torch.ones(self.d_sh)
-        for l in range(1, sh_degree + 1):
-            mask[l * l:(l + 1) ** 2] = 0.1 * 0.25 ** l
-        self.register_buffer("sh_mask", mask, persistent=False)
-
-    def forward(self, feats, extrinsics, intrinsics, near, far):
-        from pixelsplat_b200.decoder import Gaussians
-        from pixelsplat_b200.encoder.epipolar_sampler import get_world_rays, sample_image_grid
-        b, v, c, h, w = feats.shape
-        raw = self.proj(feats.permute(0, 1, 3, 4, 2)).reshape(b, v, h * w, self.gpp, -1)
-        d_logit, o_logit, s_raw, q_raw, sh = raw.split((1, 1, 3, 4, 3 * self.d_sh), dim=-1)
-        xy = sample_image_grid((h, w), feats.device).reshape(-1, 2)
-        origins, dirs = get_world_rays(xy, extrinsics, intrinsics)                  # [b, v, r, 3]
-        nr, fr = near[..., None, None], far[..., None, None]
-        u = d_logit[..., 0].sigmoid()
-        depth = 1.0 / ((1.0 - u) * (1.0 / nr - 1.0 / fr) + 1.0 / fr)                # [b, v, r, gpp]
-        means = origins[..., None, :] + dirs[..., None, :] * depth[..., None]
-        px = (1.0 / w) / intrinsics[..., 0, 0] + (1.0 / h) / intrinsics[..., 1, 1]
-        scale = (0.5 + 14.5 * s_raw.sigmoid()) * depth[..., None] * 0.1 * px[..., None, None, None]
-        q = q_raw / (q_raw.norm(dim=-1, keepdim=True) + 1e-8)
-        i, j, k, r = q.unbind(-1)
-        two = 2.0 / (q * q).sum(-1)
-        R = torch.stack([1 - two * (j * j + k * k), two * (i * j - k * r), two * (i * k + j * r),
-                         two * (i * j + k * r), 1 - two * (i * i + k * k), two * (j * k - i * r),
-                         two * (i * k - j * r), two * (j * k + i * r), 1 - two * (i * i + j * j)], -1)
-        R = R.reshape(*q.shape[:-1], 3, 3)
-        RS = R * scale[..., None, :]
-        cov = RS @ RS.transpose(-1, -2)
-        c2w = extrinsics[..., :3, :3][:, :, None, None]
-        cov = c2w @ cov @ c2w.transpose(-1, -2)
-        sh = sh.reshape(*sh.shape[:-1], 3, self.d_sh) * self.sh_mask
-        opac = o_logit[..., 0].sigmoid() / self.gpp
-        flat = lambda t: t.reshape(b, v * h * w * self.gpp, *t.shape[4:])
-        return Gaussians(flat(means), flat(cov), flat(sh), flat(opac))
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=7, help="scenes per GPU (README.md:87: batch is per GPU)")
@@ -86,13 +40,14 @@ def main():
     from pixelsplat_b200 import parallel, synthetic
     from pixelsplat_b200.decoder import DecoderSplattingCUDA, DecoderSplattingCUDACfg
     from pixelsplat_b200.encoder import EpipolarTransformer, EpipolarTransformerCfg, ImageSelfAttentionCfg
+    from pixelsplat_b200.encoder.encoder_tail import EncoderEpipolarTail, EncoderTailCfg
     rank, world, local = parallel.init_distributed()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     torch.manual_seed(0)                     # identical initial parameters on every rank
     cfg = EpipolarTransformerCfg(ImageSelfAttentionCfg(4, 10, 2, 4, 128, 128, 256), 10, 2, 4, 32, 128, 256, 4)
     enc = EpipolarTransformer(cfg, 128, num_context_views=2).to(dev)
-    head = GaussianHead(128).to(dev)
+    head = EncoderEpipolarTail(EncoderTailCfg()).to(dev)
     dec = DecoderSplattingCUDA(DecoderSplattingCUDACfg("splatting_cuda"),
                                type("D", (), {"background_color": [0.0, 0.0, 0.0]})()).to(dev)
     params = list(enc.parameters()) + list(head.parameters())
@@ -100,6 +55,7 @@ def main():
     B, T, HW = args.batch, args.target_views, args.hw
     g = torch.Generator().manual_seed(1234 + rank)          # per-rank data (main.py:106)
     feats = torch.randn(B, 2, 128, HW, HW, generator=g).to(dev)
+    images = torch.rand(B, 2, 3, HW, HW, generator=g).to(dev)
     ctx_e = torch.eye(4).repeat(B, 2, 1, 1); ctx_e[:, 1, 0, 3] = 1.0
     ctx_k = synthetic.intrinsics_re10k(2)[None].repeat(B, 1, 1, 1)
     near_v, far_v = synthetic.bounds_from_baseline(1.0, HW, HW, 3.0 * HW, 0.5)
@@ -110,6 +66,7 @@ def main():
     near_c, far_c = torch.full((B, 2), near_v, device=dev), torch.full((B, 2), far_v, device=dev)
     near_t, far_t = torch.full((B, T), near_v, device=dev), torch.full((B, T), far_v, device=dev)
 
+    context = dict(image=images, extrinsics=ctx_e, intrinsics=ctx_k, near=near_c, far=far_c)
     phases = ["encoder", "head", "render", "backward", "allreduce", "optimizer"]
     acc = {p: 0.0 for p in phases}
 
@@ -117,7 +74,7 @@ def main():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(phases) + 1)]
         ev[0].record()
         f, _ = enc(feats, ctx_e, ctx_k, near_c, far_c); ev[1].record()
-        gs = head(f, ctx_e, ctx_k, near_c, far_c); ev[2].record()
+        gs = head(f, context, global_step=0); ev[2].record()
         out = dec(gs, tgt_e, tgt_k, near_t, far_t, (HW, HW)); ev[3].record()
         loss = (out.color - target).square().mean()
         opt.zero_grad(set_to_none=True)
