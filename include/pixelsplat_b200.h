@@ -289,6 +289,14 @@ PS_API int ps_gaussian_adapter_backward(const ps_adapter_desc *desc, const ps_ad
                                         const float *d_rotations, float *d_coordinates, float *d_depths,
                                         float *d_raw, void *stream);
 
+/* Block-diagonal SH rotation matrices D(c2w) [n_views, sh_coeffs, sh_coeffs] for ps_adapter_inputs.sh_rotation
+ * (replaces /root/reference/src/misc/sh_rotation.py:10-30, row f-3): c' = D c makes the rotated function at
+ * d equal the original at R^T d, in the basis the rasterizer evaluates.  fit_dirs [n_dirs, 3] are unit
+ * directions and fit_pinv [sh_coeffs, n_dirs] the per-degree pseudo-inverse of the basis sampled there
+ * (pixelsplat_b200/sh.py builds both once, in float64).  extrinsics [n_views, 4, 4] camera-to-world. */
+PS_API int ps_sh_rotation_matrices(int32_t n_views, int32_t sh_coeffs, int32_t n_dirs, const float *extrinsics,
+                                   const float *fit_dirs, const float *fit_pinv, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

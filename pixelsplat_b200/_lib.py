@@ -86,7 +86,8 @@ EXPORTS = ("ps_version", "ps_last_error", "ps_raster_sizes_query", "ps_raster_la
            "ps_raster_forward", "ps_raster_backward", "ps_camera_setup", "ps_launch_count",
            "ps_timing_enable", "ps_timing_read", "ps_epipolar_geometry",
            "ps_epipolar_attention_forward", "ps_epipolar_attention_backward",
-           "ps_self_attention_forward", "ps_gaussian_adapter_forward", "ps_gaussian_adapter_backward")
+           "ps_self_attention_forward", "ps_gaussian_adapter_forward", "ps_gaussian_adapter_backward",
+           "ps_sh_rotation_matrices")
 
 
 class NativeLibraryMissing(ImportError):
@@ -129,6 +130,8 @@ def _load() -> ctypes.CDLL:
     lib.ps_gaussian_adapter_forward.restype = ctypes.c_int
     lib.ps_gaussian_adapter_backward.argtypes = [P(AdapterDesc), P(AdapterInputs)] + [ctypes.c_void_p] * 9
     lib.ps_gaussian_adapter_backward.restype = ctypes.c_int
+    lib.ps_sh_rotation_matrices.argtypes = [ctypes.c_int32] * 3 + [ctypes.c_void_p] * 5
+    lib.ps_sh_rotation_matrices.restype = ctypes.c_int
     for f in ("ps_raster_sizes_query", "ps_raster_layout_query", "ps_raster_forward", "ps_raster_backward"):
         getattr(lib, f).restype = ctypes.c_int
     return lib

@@ -191,12 +191,19 @@ k_gaussian_adapter_fwd(ps_adapter_desc d, ps_adapter_inputs in, float *__restric
     }
     __syncwarp();
     // ---- harmonics: the n_samples Gaussians of a ray carry the same rotated coefficients
+    // (3 sh_coeffs <= 75 floats per Gaussian: at most three 32-wide coalesced runs, held in registers
+    // and stored once per sample)
     const int sh_n = 3 * n_sh;
+    const bool has1 = lane + 32 < sh_n, has2 = lane + 64 < sh_n, has0 = lane < sh_n;
     for (int r = 0; r < rows_valid; ++r) {
         const float *src = wrows + r * row_stride + 7;
-        float *dst = harmonics + (vr0 + r) * ns * sh_n;
-        for (int j = 0; j < ns; ++j)
-            for (int k = lane; k < sh_n; k += 32) dst[j * sh_n + k] = src[k];
+        const float v0 = has0 ? src[lane] : 0.0f, v1 = has1 ? src[lane + 32] : 0.0f, v2 = has2 ? src[lane + 64] : 0.0f;
+        float *dst = harmonics + (vr0 + r) * ns * sh_n + lane;
+        for (int j = 0; j < ns; ++j, dst += sh_n) {
+            if (has0) dst[0] = v0;
+            if (has1) dst[32] = v1;
+            if (has2) dst[64] = v2;
+        }
     }
 }
 
@@ -220,13 +227,20 @@ k_gaussian_adapter_bwd(ps_adapter_desc d, ps_adapter_inputs in, const float *__r
     const size_t vr0 = (size_t)view * d.n_rays + ray0;
     float *wrows = s_rows + (size_t)warp * 32 * row_stride;
     // ---- dL/d(harmonics), summed over the ray's samples, coalesced into the gradient rows
-    for (int r = 0; r < rows_valid; ++r) {
-        float *dst = wrows + r * row_stride + 7;
-        const float *src = d_harm + (vr0 + r) * ns * sh_n;
-        for (int k = lane; k < sh_n; k += 32) {
-            float t = 0.0f;
-            for (int j = 0; j < ns; ++j) t += src[j * sh_n + k];
-            dst[k] = t;
+    {
+        const bool has0 = lane < sh_n, has1 = lane + 32 < sh_n, has2 = lane + 64 < sh_n;
+        for (int r = 0; r < rows_valid; ++r) {
+            const float *src = d_harm + (vr0 + r) * ns * sh_n + lane;
+            float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
+            for (int j = 0; j < ns; ++j, src += sh_n) {
+                if (has0) t0 += src[0];
+                if (has1) t1 += src[32];
+                if (has2) t2 += src[64];
+            }
+            float *dst = wrows + r * row_stride + 7;
+            if (has0) dst[lane] = t0;
+            if (has1) dst[lane + 32] = t1;
+            if (has2) dst[lane + 64] = t2;
         }
     }
     __syncwarp();
@@ -334,6 +348,38 @@ k_gaussian_adapter_bwd(ps_adapter_desc d, ps_adapter_inputs in, const float *__r
     unstage_sh_rows(wrows, d_raw + vr0 * raw_n, rows_valid, raw_n, row_stride, lane);
 }
 
+// D(R) for every camera: c' = D c  <=>  sum_i c'_i Y_i(d) = sum_i c_i Y_i(R^T d).  Y+ (the per-degree
+// pseudo-inverse of the basis sampled at `m` fixed directions, float64-fitted on the host once) turns
+// the basis values at the rotated directions into the block-diagonal matrix: D_l = Y+_l Y_l(R^T d).
+// One CTA per camera; the dot products accumulate in double (m = 192 terms).
+__global__ void __launch_bounds__(256)
+k_sh_rotation(int n_sh, int m, const float *__restrict__ extrinsics, const float *__restrict__ dirs,
+              const float *__restrict__ pinv, float *__restrict__ out) {
+    extern __shared__ float s_y[];                    // [m][n_sh] basis at R^T d
+    const int view = blockIdx.x, tid = threadIdx.x;
+    const float *E = extrinsics + 16 * view;
+    const int deg = n_sh >= 25 ? 4 : n_sh >= 16 ? 3 : n_sh >= 9 ? 2 : n_sh >= 4 ? 1 : 0;
+    for (int t = tid; t < m; t += blockDim.x) {
+        const float dx = dirs[3 * t], dy = dirs[3 * t + 1], dz = dirs[3 * t + 2];
+        const float x = E[0] * dx + E[4] * dy + E[8] * dz;          // R^T d  (R = E[:3,:3], row-major, stride 4)
+        const float y = E[1] * dx + E[5] * dy + E[9] * dz;
+        const float z = E[2] * dx + E[6] * dy + E[10] * dz;
+        float *row = s_y + (size_t)t * n_sh;
+        sh_for_each(deg, x, y, z, [&](int i, float v, float, float, float) { row[i] = v; });
+    }
+    __syncthreads();
+    for (int e = tid; e < n_sh * n_sh; e += blockDim.x) {
+        const int i = e / n_sh, j = e - i * n_sh;
+        int li = 0, lj = 0;
+        while ((li + 1) * (li + 1) <= i) ++li;
+        while ((lj + 1) * (lj + 1) <= j) ++lj;
+        double acc = 0.0;
+        if (li == lj)
+            for (int t = 0; t < m; ++t) acc += (double)pinv[(size_t)i * m + t] * (double)s_y[(size_t)t * n_sh + j];
+        out[(size_t)view * n_sh * n_sh + e] = (float)acc;
+    }
+}
+
 static int adapter_check(const ps_adapter_desc *d, const ps_adapter_inputs *in, const char *who) {
     if (!d || !in) { set_error("%s: null descriptor", who); return PS_ERR_INVALID_ARGUMENT; }
     if (d->n_views < 1 || d->n_rays < 1 || d->n_samples < 1 || d->n_samples > kAdMaxSamples || d->image_h < 1 || d->image_w < 1) {
@@ -400,5 +446,28 @@ extern "C" PS_API int ps_gaussian_adapter_backward(const ps_adapter_desc *desc, 
         *desc, *in, d_means, d_covariances, d_harmonics, d_scales, d_rotations, d_coordinates, d_depths, d_raw,
         row_stride);
     PS_LAUNCH_CHECK("k_gaussian_adapter_bwd");
+    return PS_OK;
+}
+
+extern "C" PS_API int ps_sh_rotation_matrices(int32_t n_views, int32_t sh_coeffs, int32_t n_dirs,
+                                              const float *extrinsics, const float *fit_dirs,
+                                              const float *fit_pinv, float *out, void *stream) {
+    using namespace ps;
+    if (n_views < 1 || n_dirs < 1 || n_dirs > 512 || !extrinsics || !fit_dirs || !fit_pinv || !out) {
+        set_error("ps_sh_rotation_matrices: bad argument");
+        return PS_ERR_INVALID_ARGUMENT;
+    }
+    if (sh_coeffs != 1 && sh_coeffs != 4 && sh_coeffs != 9 && sh_coeffs != 16 && sh_coeffs != 25) {
+        set_error("ps_sh_rotation_matrices: sh_coeffs must be (degree + 1)^2 with degree <= 4 (got %d)", sh_coeffs);
+        return PS_ERR_UNSUPPORTED;
+    }
+    static bool attr = false;
+    if (!attr) {
+        PS_CUDA_CHECK(cudaFuncSetAttribute(k_sh_rotation, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr = true;
+    }
+    k_sh_rotation<<<n_views, 256, sizeof(float) * n_dirs * sh_coeffs, static_cast<cudaStream_t>(stream)>>>(
+        sh_coeffs, n_dirs, extrinsics, fit_dirs, fit_pinv, out);
+    PS_LAUNCH_CHECK("k_sh_rotation");
     return PS_OK;
 }

@@ -21,7 +21,7 @@ import torch
 from torch import Tensor, nn
 
 from .. import _lib
-from ..sh import rotate_sh, sh_rotation_matrices
+from ..sh import camera_sh_rotations, rotate_sh
 
 
 @dataclass
@@ -155,8 +155,7 @@ class GaussianAdapter(nn.Module):
         nv, nr = b * v, r * srf
         E = extrinsics.expand(b, v, 1, 1, 1, 4, 4).reshape(nv, 4, 4)
         K = intrinsics.expand(b, v, 1, 1, 1, 3, 3).reshape(nv, 3, 3)
-        with torch.no_grad():
-            D = sh_rotation_matrices(E[:, :3, :3].detach(), self.cfg.sh_degree).float()
+        D = camera_sh_rotations(E, self.cfg.sh_degree)
         coords = coordinates.expand(b, v, r, srf, 1, 2).reshape(nv, nr, 2)
         means, cov, harm, scales, rot = _GaussianAdapterFn.apply(
             E.detach(), K.detach(), D, self.sh_mask, coords, depths.reshape(nv, nr, spp),

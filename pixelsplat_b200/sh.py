@@ -80,3 +80,42 @@ def rotate_sh(sh_coefficients: Tensor, rotations: Tensor) -> Tensor:
     degree = int(round(n ** 0.5)) - 1
     D = sh_rotation_matrices(rotations, degree)
     return torch.einsum("...ij,...j->...i", D, sh_coefficients)
+
+
+# ---- device-side construction (one tiny kernel per step: csrc/gaussian_adapter.cu `k_sh_rotation`) --------
+_FIT_CACHE: dict = {}
+
+
+def fit_operators(device, degree: int = 4) -> tuple[Tensor, Tensor]:
+    """(fit directions [m, 3], per-degree pseudo-inverse of the basis there [n, m]), float32 on `device`,
+    built once in float64: D_l(R) = pinv_l @ Y_l(R^T dirs)."""
+    key = (str(device), degree)
+    if key not in _FIT_CACHE:
+        dirs = _fit_directions()
+        Y = sh_basis(dirs, degree)                                       # [m, n] float64
+        pinv = torch.zeros((Y.shape[1], Y.shape[0]), dtype=torch.float64)
+        for l in range(degree + 1):
+            s = slice(l * l, (l + 1) ** 2)
+            pinv[s] = torch.linalg.pinv(Y[:, s])
+        _FIT_CACHE[key] = (dirs.float().contiguous().to(device), pinv.float().contiguous().to(device))
+    return _FIT_CACHE[key]
+
+
+def camera_sh_rotations(extrinsics: Tensor, degree: int = 4) -> Tensor:
+    """extrinsics [n, 4, 4] (CUDA, camera-to-world) -> D [n, (degree+1)^2, (degree+1)^2], float32, via the
+    library kernel (no host synchronisation; equals sh_rotation_matrices(extrinsics[:, :3, :3]) to ~1e-6)."""
+    import ctypes
+
+    from . import _lib
+    if not extrinsics.is_cuda:
+        raise ValueError("pixelsplat_b200 has no CPU path: camera_sh_rotations needs a CUDA tensor")
+    E = extrinsics.detach().contiguous().float()
+    n = (degree + 1) ** 2
+    dirs, pinv = fit_operators(E.device, degree)
+    out = torch.empty((E.shape[0], n, n), dtype=torch.float32, device=E.device)
+    stream = torch.cuda.current_stream(E.device)
+    rc = _lib.lib.ps_sh_rotation_matrices(E.shape[0], n, dirs.shape[0], ctypes.c_void_p(E.data_ptr()),
+                                          ctypes.c_void_p(dirs.data_ptr()), ctypes.c_void_p(pinv.data_ptr()),
+                                          ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(stream.cuda_stream))
+    _lib.check(rc, "ps_sh_rotation_matrices")
+    return out

@@ -47,8 +47,8 @@ def test_fused_adapter_matches_reference(case, monkeypatch):
     from pixelsplat_b200 import _lib
     from pixelsplat_b200.encoder import gaussian_adapter as ga
     # factor the SH rotation out exactly as the golden generator did
-    monkeypatch.setattr(ga, "sh_rotation_matrices",
-                        lambda R, degree: torch.eye((degree + 1) ** 2, device=R.device).expand(*R.shape[:-2], -1, -1))
+    monkeypatch.setattr(ga, "camera_sh_rotations",
+                        lambda E, degree: torch.eye((degree + 1) ** 2, device=E.device).repeat(E.shape[0], 1, 1))
     before = _lib.lib.ps_launch_count()
     g, grads = _run(_adapter(), gu.adapter_case(case=case))
     assert _lib.lib.ps_launch_count() == before + 2          # one forward, one backward kernel
@@ -79,6 +79,15 @@ def test_fused_equals_explicit_path_with_rotation(degree, r, spp):
         assert a.shape == b.shape and rel_err(a, b) < 5e-6, k
     for k in LEAVES:
         assert rel_err(grads_f[k].cpu().numpy(), grads_e[k].cpu().numpy()) < 2e-5, k
+
+
+def test_device_rotation_matrices_equal_the_float64_fit():
+    from pixelsplat_b200 import sh
+    ext = gu.camera_rig(3, 3, "diverging")[0].reshape(9, 4, 4)
+    for degree in range(5):
+        D = sh.camera_sh_rotations(ext.to(DEV, torch.float32), degree)
+        ref = sh.sh_rotation_matrices(ext[:, :3, :3], degree)
+        assert D.shape == ref.shape and (D.cpu().double() - ref).abs().max() < 2e-6
 
 
 def test_two_surfaces_and_unusual_broadcast_fall_back():
