@@ -120,6 +120,30 @@ __device__ __forceinline__ void sh_rotate_row(float *row, const float *sD, int n
     if (n_sh >= 25) sh_rotate_block<4, kTranspose>(row, sD, n_sh);
 }
 
+// Coalesced copy of `rows` consecutive n-float rows into padded shared rows, four independent 32-wide
+// loads in flight per lane (stage_sh_rows issues them one at a time; this kernel is latency-bound at
+// ~20 warps per SM, so memory-level parallelism per warp is what moves it).
+__device__ __forceinline__ void stage_rows_x4(const float *__restrict__ src, float *dst, int rows, int n,
+                                              int row_stride, int lane) {
+    const int total = rows * n;
+    int r = lane / n, c = lane - r * n;
+    const int step_r = 32 / n, step_c = 32 - step_r * n;
+    for (int e = lane; e < total; e += 128) {
+        float v[4];
+        int off[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            off[q] = r * row_stride + c;
+            v[q] = (e + 32 * q < total) ? __ldg(src + e + 32 * q) : 0.0f;
+            r += step_r; c += step_c;
+            if (c >= n) { c -= n; ++r; }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (e + 32 * q < total) dst[off[q]] = v[q];
+    }
+}
+
 __global__ void __launch_bounds__(kAdThreads)
 k_gaussian_adapter_fwd(ps_adapter_desc d, ps_adapter_inputs in, float *__restrict__ means, float *__restrict__ cov,
                        float *__restrict__ harmonics, float *__restrict__ scales, float *__restrict__ rotations,
@@ -137,7 +161,7 @@ k_gaussian_adapter_fwd(ps_adapter_desc d, ps_adapter_inputs in, float *__restric
     const int rows_valid = min(32, d.n_rays - ray0);
     const size_t vr0 = (size_t)view * d.n_rays + ray0;
     float *wrows = s_rows + (size_t)warp * 32 * row_stride;
-    stage_sh_rows(in.raw + vr0 * raw_n, wrows, rows_valid, raw_n, row_stride, lane);
+    stage_rows_x4(in.raw + vr0 * raw_n, wrows, rows_valid, raw_n, row_stride, lane);
     __syncwarp();
     const bool live = lane < rows_valid;
     float *row = wrows + lane * row_stride;
@@ -355,10 +379,12 @@ k_gaussian_adapter_bwd(ps_adapter_desc d, ps_adapter_inputs in, const float *__r
 __global__ void __launch_bounds__(256)
 k_sh_rotation(int n_sh, int m, const float *__restrict__ extrinsics, const float *__restrict__ dirs,
               const float *__restrict__ pinv, float *__restrict__ out) {
-    extern __shared__ float s_y[];                    // [m][n_sh] basis at R^T d
+    extern __shared__ float s_y[];                    // [m][n_sh] basis at R^T d, then [n_sh][m] pinv
+    float *s_pinv = s_y + (size_t)m * n_sh;
     const int view = blockIdx.x, tid = threadIdx.x;
     const float *E = extrinsics + 16 * view;
     const int deg = n_sh >= 25 ? 4 : n_sh >= 16 ? 3 : n_sh >= 9 ? 2 : n_sh >= 4 ? 1 : 0;
+    for (int e = tid; e < n_sh * m; e += blockDim.x) s_pinv[e] = pinv[e];
     for (int t = tid; t < m; t += blockDim.x) {
         const float dx = dirs[3 * t], dy = dirs[3 * t + 1], dz = dirs[3 * t + 2];
         const float x = E[0] * dx + E[4] * dy + E[8] * dz;          // R^T d  (R = E[:3,:3], row-major, stride 4)
@@ -373,10 +399,19 @@ k_sh_rotation(int n_sh, int m, const float *__restrict__ extrinsics, const float
         int li = 0, lj = 0;
         while ((li + 1) * (li + 1) <= i) ++li;
         while ((lj + 1) * (lj + 1) <= j) ++lj;
-        double acc = 0.0;
-        if (li == lj)
-            for (int t = 0; t < m; ++t) acc += (double)pinv[(size_t)i * m + t] * (double)s_y[(size_t)t * n_sh + j];
-        out[(size_t)view * n_sh * n_sh + e] = (float)acc;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        if (li == lj) {
+            const float *pr = s_pinv + (size_t)i * m, *yc = s_y + j;
+            int t = 0;
+            for (; t + 3 < m; t += 4) {
+                a0 += (double)pr[t] * (double)yc[(size_t)t * n_sh];
+                a1 += (double)pr[t + 1] * (double)yc[(size_t)(t + 1) * n_sh];
+                a2 += (double)pr[t + 2] * (double)yc[(size_t)(t + 2) * n_sh];
+                a3 += (double)pr[t + 3] * (double)yc[(size_t)(t + 3) * n_sh];
+            }
+            for (; t < m; ++t) a0 += (double)pr[t] * (double)yc[(size_t)t * n_sh];
+        }
+        out[(size_t)view * n_sh * n_sh + e] = (float)((a0 + a1) + (a2 + a3));
     }
 }
 
@@ -463,10 +498,10 @@ extern "C" PS_API int ps_sh_rotation_matrices(int32_t n_views, int32_t sh_coeffs
     }
     static bool attr = false;
     if (!attr) {
-        PS_CUDA_CHECK(cudaFuncSetAttribute(k_sh_rotation, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        PS_CUDA_CHECK(cudaFuncSetAttribute(k_sh_rotation, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         attr = true;
     }
-    k_sh_rotation<<<n_views, 256, sizeof(float) * n_dirs * sh_coeffs, static_cast<cudaStream_t>(stream)>>>(
+    k_sh_rotation<<<n_views, 256, 2 * sizeof(float) * n_dirs * sh_coeffs, static_cast<cudaStream_t>(stream)>>>(
         sh_coeffs, n_dirs, extrinsics, fit_dirs, fit_pinv, out);
     PS_LAUNCH_CHECK("k_sh_rotation");
     return PS_OK;
