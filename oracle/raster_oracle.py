@@ -11,7 +11,6 @@ Nothing under pixelsplat_b200/ imports this module.
 from __future__ import annotations
 
 import ctypes
-import os
 import subprocess
 from dataclasses import dataclass
 from pathlib import Path

@@ -16,7 +16,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import PS_COV_3X3, PS_COV_TRIU6, PS_SH_3M, PS_SH_M3, TILE
+from ._lib import PS_COV_3X3, PS_COV_TRIU6, PS_SH_M3, TILE
 
 # ------------------------------------------------------------------ instance-capacity policy
 # The binning buffers are sized for `capacity` (tile, Gaussian) instances.  The exact count is

@@ -14,7 +14,6 @@ Everything is generated on the CPU with a fixed seed; callers move tensors where
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
 
 import torch

@@ -23,7 +23,6 @@ import sys
 from pathlib import Path
 
 import torch
-from torch import nn
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
