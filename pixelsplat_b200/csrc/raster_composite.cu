@@ -79,6 +79,46 @@ __device__ __forceinline__ void stage_store(StageBuf &s, int slot, const StagedR
     s.ext[slot] = alpha_extent(r.co);
 }
 
+// Warp-uniform FIFO of up to three staged-slot indices carried from one 32-entry cull chunk to the
+// next.  The backward evaluation loop consumes FOUR list entries per iteration (one transposed
+// reduction serves all four); a chunk leaves 6.4 hits on average, so draining every chunk separately
+// ran one iteration in five half empty.  With the carry
+// only the last chunk of a 256-entry stage can end on a partial group.  Order is preserved (carried
+// entries precede the new chunk's).
+struct HitCarry {
+    uint32_t c0, c1, c2;
+    int n;
+};
+
+__device__ __forceinline__ void carry_push_all(HitCarry &c, uint32_t &mask, uint32_t jb) {
+    while (mask) {
+        const uint32_t j = jb + (uint32_t)(__ffs(mask) - 1);
+        mask &= mask - 1;
+        if (c.n == 0) c.c0 = j;
+        else if (c.n == 1) c.c1 = j;
+        else c.c2 = j;
+        ++c.n;
+    }
+}
+
+// Next four entries: carried ones first, then the lowest set bits of `mask`; unused slots point at
+// the (valid) slot jb with has = false.
+__device__ __forceinline__ void take4(HitCarry &c, uint32_t &mask, uint32_t jb, uint32_t (&jx)[4], bool (&has)[4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (q < c.n) {
+            jx[q] = q == 0 ? c.c0 : q == 1 ? c.c1 : c.c2;
+            has[q] = true;
+        } else {
+            has[q] = mask != 0;
+            const int bq = has[q] ? __ffs(mask) - 1 : 0;
+            mask &= mask - 1;
+            jx[q] = jb + (uint32_t)bq;
+        }
+    }
+    c.n = 0;
+}
+
 __global__ void __launch_bounds__(kCompThreads)
 k_composite_fwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                 const unsigned long long *__restrict__ keys, float *__restrict__ final_T,
@@ -124,7 +164,8 @@ k_composite_fwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                 uint32_t mask = __ballot_sync(0xffffffffu, hit);
                 // four entries per iteration: their power / exp evaluations are independent, only
                 // the transmittance update chains (the warp has few peers to hide latency behind:
-                // a 256x256 view is just 2048 warps on 148 SMs)
+                // a 256x256 view is just 2048 warps on 148 SMs).  (Carrying partial groups across
+                // chunks as the backward does costs the forward more in bookkeeping than it saves.)
                 while (mask) {
                     uint32_t jx[4];
                     bool has[4];
@@ -408,6 +449,7 @@ k_composite_bwd(Dims d, Geom geo, const float *__restrict__ bg_all,
             nxt = stage_load(geo, gbase, (uint32_t)keys[start + (hi - n_here - 1u - (uint32_t)tid)]);
         for (int i = tid; i < (kCompThreads / 32) * kStage * 10; i += kCompThreads) s_acc_all[i] = 0.0f;
         __syncthreads();
+        HitCarry carry = {0u, 0u, 0u, 0};
         for (uint32_t jb = 0; jb < n_here; jb += 32) {
             const uint32_t j = jb + lane;
             bool hit = false;
@@ -416,20 +458,15 @@ k_composite_bwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                 hit = (c.x + e.x >= rx0) && (c.x - e.x <= rx1) && (c.y + e.y >= ry0) && (c.y - e.y <= ry1);
             }
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            const bool last_chunk = jb + 32u >= n_here;
             // four list entries per iteration: their exp / gradient math is independent (only the
             // cheap T / colour-behind recurrences chain), which gives the scheduler something to
             // issue while shuffles are in flight (a 256x256 view is 14 warps per SM), and one
             // 32-wide transposed shuffle reduction serves all four
-            while (mask) {
+            while (carry.n + __popc(mask) >= 4 || (last_chunk && (carry.n != 0 || mask != 0u))) {
                 uint32_t jx[4];
                 bool has[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    has[q] = mask != 0;
-                    const int bq = has[q] ? __ffs(mask) - 1 : 0;
-                    mask &= mask - 1;
-                    jx[q] = jb + (uint32_t)bq;
-                }
+                take4(carry, mask, jb, jx, has);
                 float v[32], op[4];
                 unsigned any = 0;
 #pragma unroll
@@ -454,6 +491,7 @@ k_composite_bwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                 if (live_q && k == 0) s_acc[jq][8] += opt;
                 __syncwarp();
             }
+            carry_push_all(carry, mask, jb);              // fewer than four left: they join the next chunk
         }
         __syncthreads();
         if ((uint32_t)tid < n_here) {
