@@ -443,11 +443,10 @@ extern "C" PS_API int ps_gaussian_adapter_forward(const ps_adapter_desc *desc, c
     if (!means || !covariances || !harmonics) { set_error("ps_gaussian_adapter_forward: null output pointer"); return PS_ERR_INVALID_ARGUMENT; }
     const int raw_n = 7 + 3 * desc->sh_coeffs, row_stride = raw_n | 1;
     const size_t smem = sizeof(float) * kAdThreads * row_stride;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_devices = 0;
+    if (first_use_on_device(attr_devices)) {
         PS_CUDA_CHECK(cudaFuncSetAttribute(k_gaussian_adapter_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         PS_CUDA_CHECK(cudaFuncSetAttribute(k_gaussian_adapter_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr = true;
     }
     dim3 grid((desc->n_rays + kAdThreads - 1) / kAdThreads, desc->n_views);
     k_gaussian_adapter_fwd<<<grid, kAdThreads, smem, static_cast<cudaStream_t>(stream)>>>(
@@ -470,11 +469,10 @@ extern "C" PS_API int ps_gaussian_adapter_backward(const ps_adapter_desc *desc, 
     }
     const int raw_n = 7 + 3 * desc->sh_coeffs, row_stride = raw_n | 1;
     const size_t smem = sizeof(float) * kAdThreads * row_stride;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_devices = 0;
+    if (first_use_on_device(attr_devices)) {
         PS_CUDA_CHECK(cudaFuncSetAttribute(k_gaussian_adapter_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         PS_CUDA_CHECK(cudaFuncSetAttribute(k_gaussian_adapter_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr = true;
     }
     dim3 grid((desc->n_rays + kAdThreads - 1) / kAdThreads, desc->n_views);
     k_gaussian_adapter_bwd<<<grid, kAdThreads, smem, static_cast<cudaStream_t>(stream)>>>(
@@ -496,10 +494,9 @@ extern "C" PS_API int ps_sh_rotation_matrices(int32_t n_views, int32_t sh_coeffs
         set_error("ps_sh_rotation_matrices: sh_coeffs must be (degree + 1)^2 with degree <= 4 (got %d)", sh_coeffs);
         return PS_ERR_UNSUPPORTED;
     }
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_devices = 0;
+    if (first_use_on_device(attr_devices)) {
         PS_CUDA_CHECK(cudaFuncSetAttribute(k_sh_rotation, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-        attr = true;
     }
     k_sh_rotation<<<n_views, 256, 2 * sizeof(float) * n_dirs * sh_coeffs, static_cast<cudaStream_t>(stream)>>>(
         sh_coeffs, n_dirs, extrinsics, fit_dirs, fit_pinv, out);

@@ -52,6 +52,17 @@ enum Mark { kMarkFwdStart = 0, kMarkPreprocess, kMarkScatter, kMarkSort, kMarkCo
 void mark(int id, cudaStream_t st);
 void count_launch();
 
+// Once-per-DEVICE flags (a host process may drive several GPUs; kernel attributes and the library's
+// side stream are per device).  `mask` is a caller-owned static, one bit per device ordinal.
+inline bool first_use_on_device(unsigned long long &mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
+
 #define PS_CUDA_CHECK(expr)                                                              \
     do {                                                                                 \
         cudaError_t _e = (expr);                                                         \

@@ -34,14 +34,22 @@ void mark(int id, cudaStream_t st) {
 
 // Side stream for work that is independent of the critical path (gradient zero-fill overlapping
 // the composite backward).  Fork/join with events, which also captures cleanly into CUDA graphs.
-static cudaStream_t g_side = nullptr;
-static cudaEvent_t g_fork = nullptr, g_join = nullptr;
+// The library's side stream and its fork / join events, one set per device ordinal (created on first
+// use on that device; a host process may drive several GPUs).
+struct SideCtx {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideCtx g_side_ctx[64];
 
-static int side_ready() {
-    if (g_side) return PS_OK;
-    PS_CUDA_CHECK(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
-    PS_CUDA_CHECK(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
-    PS_CUDA_CHECK(cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming));
+static int side_ready(SideCtx *&ctx) {
+    int dev = 0;
+    PS_CUDA_CHECK(cudaGetDevice(&dev));
+    ctx = &g_side_ctx[dev & 63];
+    if (ctx->side) return PS_OK;
+    PS_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    PS_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming));
+    PS_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->join, cudaEventDisableTiming));
     return PS_OK;
 }
 
@@ -245,18 +253,19 @@ PS_API int ps_raster_forward(const ps_raster_desc *desc, const ps_raster_inputs 
     uint32_t *n_contrib = reinterpret_cast<uint32_t *>(static_cast<char *>(state->image) + L.off.n_contrib);
 
     mark(kMarkFwdStart, st);
-    if ((rc = side_ready())) return rc;
+    SideCtx *sc = nullptr;
+    if ((rc = side_ready(sc))) return rc;
     if ((rc = launch_preprocess(d, I, g, st))) return rc;
     mark(kMarkPreprocess, st);
     // fork: SH -> RGB of the on-screen Gaussians runs beside the binning (scan / scatter / sort);
     // the two only meet again in the compositor
-    PS_CUDA_CHECK(cudaEventRecord(g_fork, st));
-    PS_CUDA_CHECK(cudaStreamWaitEvent(g_side, g_fork, 0));
-    if ((rc = launch_sh_color(d, I, g, g_side))) return rc;
-    PS_CUDA_CHECK(cudaEventRecord(g_join, g_side));
+    PS_CUDA_CHECK(cudaEventRecord(sc->fork, st));
+    PS_CUDA_CHECK(cudaStreamWaitEvent(sc->side, sc->fork, 0));
+    if ((rc = launch_sh_color(d, I, g, sc->side))) return rc;
+    PS_CUDA_CHECK(cudaEventRecord(sc->join, sc->side));
     if ((rc = launch_binning(d, g, keys, keys_alt, desc->sort_impl, desc->sort_segment_hint, st))) return rc;
     mark(kMarkSort, st);
-    PS_CUDA_CHECK(cudaStreamWaitEvent(st, g_join, 0));   // join
+    PS_CUDA_CHECK(cudaStreamWaitEvent(st, sc->join, 0));   // join
     if (n_instances_host)
         PS_CUDA_CHECK(cudaMemcpyAsync(n_instances_host, g.n_instances, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     if ((rc = launch_composite_forward(d, I, g, keys, final_T, n_contrib, out_color, st))) return rc;
@@ -298,17 +307,18 @@ PS_API int ps_raster_backward(const ps_raster_desc *desc, const ps_raster_inputs
     vg.d_conic = reinterpret_cast<float4 *>(sb + align_up(vp * 8));
     vg.d_color = reinterpret_cast<float4 *>(sb + align_up(vp * 8) + align_up(vp * 16));
     mark(kMarkBwdStart, st);
-    if ((rc = side_ready())) return rc;
+    SideCtx *sc = nullptr;
+    if ((rc = side_ready(sc))) return rc;
     // fork: zero the output gradients on the side stream while the composite backward runs
-    PS_CUDA_CHECK(cudaEventRecord(g_fork, st));
-    PS_CUDA_CHECK(cudaStreamWaitEvent(g_side, g_fork, 0));
-    if ((rc = launch_gradient_fill(d, *grads, g_side))) return rc;
-    PS_CUDA_CHECK(cudaEventRecord(g_join, g_side));
+    PS_CUDA_CHECK(cudaEventRecord(sc->fork, st));
+    PS_CUDA_CHECK(cudaStreamWaitEvent(sc->side, sc->fork, 0));
+    if ((rc = launch_gradient_fill(d, *grads, sc->side))) return rc;
+    PS_CUDA_CHECK(cudaEventRecord(sc->join, sc->side));
     PS_CUDA_CHECK(cudaMemsetAsync(scratch, 0, L.sizes.backward_bytes, st));
     mark(kMarkBwdZero, st);
     if ((rc = launch_composite_backward(d, I, g, keys, final_T, n_contrib, d_color, vg, st))) return rc;
     mark(kMarkCompositeBwd, st);
-    PS_CUDA_CHECK(cudaStreamWaitEvent(st, g_join, 0));   // join
+    PS_CUDA_CHECK(cudaStreamWaitEvent(st, sc->join, 0));   // join
     if ((rc = launch_preprocess_backward(d, I, g, vg, *grads, st))) return rc;
     mark(kMarkPreprocessBwd, st);
     return PS_OK;

@@ -319,11 +319,10 @@ int launch_binning(const Dims &d, const Geom &g, unsigned long long *keys,
     k_tile_scan<<<1, kScanThreads, 0, st>>>(n_seg, g.tile_count, g.tile_start, g.tile_cursor, g.n_instances);
     PS_LAUNCH_CHECK("k_tile_scan");
     const int use_smem = d.tiles <= kScatterMaxSmemTiles;
-    static bool scatter_attr = false;
-    if (!scatter_attr) {
+    static unsigned long long scatter_attr_devices = 0;
+    if (first_use_on_device(scatter_attr_devices)) {
         PS_CUDA_CHECK(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)(2 * sizeof(uint32_t) * kScatterMaxSmemTiles)));
-        scatter_attr = true;
     }
     dim3 sgrid((d.P + kScatterThreads - 1) / kScatterThreads, d.S * d.V);
     k_scatter<<<sgrid, kScatterThreads, use_smem ? 2 * sizeof(uint32_t) * d.tiles : 0, st>>>(d, g, keys, use_smem);
@@ -358,11 +357,10 @@ int launch_binning(const Dims &d, const Geom &g, unsigned long long *keys,
         const long long want = (long long)segment_hint + segment_hint / 4;
         while (cap < want && cap < 8192) cap <<= 1;
     }
-    static bool battr = false;
-    if (!battr) {
+    static unsigned long long battr_devices = 0;
+    if (first_use_on_device(battr_devices)) {
         PS_CUDA_CHECK(cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)sort_smem_bytes(8192)));
-        battr = true;
     }
     k_tile_sort<<<n_seg, kSortThreads, sort_smem_bytes(cap), st>>>(
         g.tile_start, g.tile_count, g.n_instances, d.capacity, keys, keys_alt, cap, id_bits);

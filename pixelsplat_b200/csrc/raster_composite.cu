@@ -535,10 +535,9 @@ int launch_composite_backward(const Dims &d, const Inputs &in, const Geom &g,
                               cudaStream_t st) {
     dim3 grid(d.tiles, d.S * d.V);
     const size_t acc_bytes = sizeof(float) * (kCompThreads / 32) * kStage * 10;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_devices = 0;
+    if (first_use_on_device(attr_devices)) {
         PS_CUDA_CHECK(cudaFuncSetAttribute(k_composite_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
-        attr = true;
     }
     k_composite_bwd<<<grid, kCompThreads, acc_bytes, st>>>(d, g, in.bg, keys, final_T, n_contrib, d_color, vg);
     PS_LAUNCH_CHECK("k_composite_bwd");

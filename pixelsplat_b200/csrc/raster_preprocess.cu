@@ -202,10 +202,9 @@ int launch_sh_color(const Dims &d, const Inputs &in, const Geom &g, cudaStream_t
     // the pair count lives on the device: launch for the worst case, surplus warps exit at once
     const int row_stride = (3 * d.M) | 1;
     const size_t smem = sizeof(float) * kShThreads * row_stride;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_devices = 0;
+    if (first_use_on_device(attr_devices)) {
         PS_CUDA_CHECK(cudaFuncSetAttribute(k_sh_color, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr = true;
     }
     const long long pairs = (long long)d.S * d.V * d.P;
     k_sh_color<<<(unsigned)((pairs + kShThreads - 1) / kShThreads), kShThreads, smem, st>>>(d, in, g, row_stride);

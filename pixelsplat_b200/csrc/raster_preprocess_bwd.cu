@@ -209,10 +209,9 @@ int launch_preprocess_backward(const Dims &d, const Inputs &in, const Geom &g, c
                                const ps_raster_grads &out, cudaStream_t st) {
     const int row_stride = d.M > 0 ? ((3 * d.M) | 1) : 1;   // odd word count: conflict-free per-lane rows
     const size_t smem = d.M > 0 ? sizeof(float) * kPreBwdThreads * row_stride * (d.V == 1 ? 1 : 2) : 0;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_devices = 0;
+    if (first_use_on_device(attr_devices)) {
         PS_CUDA_CHECK(cudaFuncSetAttribute(k_preprocess_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr = true;
     }
     const long long sp = (long long)d.S * d.P;               // worst case; surplus warps exit at once
     k_preprocess_bwd<<<(unsigned)((sp + kPreBwdThreads - 1) / kPreBwdThreads), kPreBwdThreads, smem, st>>>(

@@ -307,10 +307,9 @@ extern "C" PS_API int ps_self_attention_forward(int32_t n_images, int32_t tokens
     }
     if (((uintptr_t)qkv | (uintptr_t)out) & 15) { set_error("ps_self_attention_forward: pointers must be 16-byte aligned"); return PS_ERR_INVALID_ARGUMENT; }
     const size_t smem = 192 * 1024 + 64 + 128 * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_devices = 0;
+    if (first_use_on_device(attr_devices)) {
         PS_CUDA_CHECK(cudaFuncSetAttribute(k_self_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
     }
     dim3 grid(2, heads, n_images);
     k_self_attention_tc<<<grid, kSaThreads, smem, static_cast<cudaStream_t>(stream)>>>(
