@@ -64,7 +64,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -74,7 +74,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
+
+    def count_between(self, t0: float, t1: float) -> int:
+        return sum(1 for t, _ in self.rows if t0 <= t <= t1)
 
     def __exit__(self, *exc):
         if self.proc is not None:
@@ -84,10 +87,12 @@ class ClockSampler:
             except subprocess.TimeoutExpired:
                 self.proc.kill()
 
-    def summary(self):
+    def summary(self, t0: float = float("-inf"), t1: float = float("inf"), window: str = "timed region"):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if not (t0 <= t <= t1):
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -96,9 +101,9 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": window}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 CONTEXT_VIEWS = 2
@@ -212,10 +217,31 @@ def run_reference(args, rank, world):
                 "un-vendored dependency that cannot be installed offline; this arm is the CPU "
                 "restatement (kind=port), not the reference's CUDA path",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_OUT = None
+
+
+def isolate_stdout():
+    """stdout must carry exactly one JSON line.  Libraries write to file descriptor 1 behind Python's back
+    (NCCL prints its version banner there at NCCL_DEBUG=VERSION / WARN), so keep a private duplicate of the
+    real stdout for the result line and point fd 1 at stderr for everything else."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    isolate_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
@@ -250,10 +276,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (printed to stdout at
-        # NCCL_DEBUG=VERSION) out of it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # (NCCL's version banner goes to fd 1: see isolate_stdout)
         dist.init_process_group("nccl", device_id=dev)
 
     from pixelsplat_b200 import _lib, rasterizer
@@ -296,19 +319,36 @@ def main():
     barrier()
     launches0 = _lib.lib.ps_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        barrier()
-        e0.record()
+    def run_steps(n):
         if graphs is not None:
-            for i in range(K):
+            for i in range(n):
                 graphs[i % args.pool][0].replay()
         else:
-            for i in range(K):
+            for i in range(n):
                 render_step(pool_dev[i % args.pool], d_img, V)
+
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        t_begin = time.monotonic()
+        e0.record()
+        run_steps(K)
         e1.record()
         barrier()
+        t_end = time.monotonic()
+        launches_timed = _lib.lib.ps_launch_count() - launches0
+        clock_window = "timed region"
+        if clk.proc is not None and clk.count_between(t_begin, t_end) < 3:
+            # the timed region is shorter than a few nvidia-smi sampling periods: keep the SAME load running,
+            # untimed, until the sampler has seen it (at most ~1 s), and say so
+            t_c = time.monotonic()
+            while time.monotonic() - t_c < 1.0 and clk.count_between(t_begin, time.monotonic()) < 6:
+                run_steps(min(K, 100))
+                torch.cuda.synchronize()
+            t_end = time.monotonic()
+            clock_window = "timed region + identical untimed continuation (timed region shorter than the sampling period)"
+        clocks = clk.summary(t_begin, t_end, clock_window)
     ms_total = e0.elapsed_time(e1)
-    launches = (launches_per_step * K) if graphs is not None else (_lib.lib.ps_launch_count() - launches0)
+    launches = (launches_per_step * K) if graphs is not None else launches_timed
     if graphs is not None:
         for _, _, states in graphs:      # capacity check of the replayed forwards (count is in pinned memory)
             for st_ in states:
@@ -488,10 +528,10 @@ def main():
                              "inputs larger than L2, no flush",
                        "capacity_check": "deferred (verified at backward)",
                        "launch": "eager python" if args.no_graph else "one CUDA graph per scene (fwd+bwd), replayed"},
-            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "stage_ms": stage_ms, "workload_stats": stats, "throughput_concurrent_streams": concurrent, "throughput_batched_views": batched,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -29,9 +29,6 @@ def init_distributed(backend: str | None = None) -> tuple[int, int, int]:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         kwargs = {}
         if backend == "nccl":
-            import os
-            if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-                os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout
             torch.cuda.set_device(local)
             kwargs["device_id"] = torch.device("cuda", local)
         dist.init_process_group(backend, **kwargs)

@@ -65,3 +65,17 @@ def test_gloo_world2_collectives():
     assert res[0][1] == res[1][1] and res[0][1] >= 2     # several buckets
     assert res[0][2] and res[1][2]
     assert res[0][3] == pytest.approx(10.0)              # 2 ranks x 10 units / 2 s
+
+
+def test_bench_stdout_carries_only_the_result_line():
+    """bench.py's contract is ONE JSON line on stdout; anything a library writes to fd 1 (NCCL's version
+    banner) must end up on stderr."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    code = ("import bench, os; bench.isolate_stdout(); os.write(1, b'NCCL version 2.x\\n'); "
+            "print('stray print'); bench.emit({'value': 1})")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, check=True)
+    assert r.stdout == '{"value": 1}\n'
+    assert "NCCL version" in r.stderr and "stray print" in r.stderr
