@@ -495,7 +495,7 @@ def main():
         roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
                     "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
                     "note": "one 256x256 view is 0.3 waves of the machine: this kernel is issue/latency-bound "
-                            "(59-67 % issue-active, DRAM throughput ~1 %), so the HBM fraction is small by "
+                            "(56-67 % issue-active, DRAM traffic below the algorithmic bytes), so the HBM fraction is small by "
                             "construction; see profiles/README.md",
                     "peak_source": f"{pk_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                     "algorithmic_bytes_per_launch": V * ab[dom], "avg_launch_ms": stage_ms[dom],
