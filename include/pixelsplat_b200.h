@@ -118,6 +118,11 @@ typedef struct ps_raster_layout {
     /* image */
     size_t final_T;       /* f32  [S*V*H*W]                                                    */
     size_t n_contrib;     /* u32  [S*V*H*W]                                                    */
+    /* appended in round 2 (struct grows at the end only) */
+    size_t cull;          /* geom: f32x4 [S*V*P] (x, y, half-extent x, half-extent y) of the
+                             alpha >= 1/255 box -- the compositor's cull record                */
+    size_t color;         /* image: f32 [S*V*3*H*W] copy of the rendered colour (the backward's
+                             forward-order prefix form needs C . dL/dC per pixel)              */
 } ps_raster_layout;
 
 typedef struct ps_raster_grads {

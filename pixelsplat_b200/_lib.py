@@ -52,7 +52,7 @@ class RasterLayout(ctypes.Structure):
     _fields_ = [(n, ctypes.c_size_t) for n in (
         "depth", "radii", "xy", "conic_opacity", "rgb", "rect", "clamped", "tile_count",
         "tile_start", "tile_cursor", "n_instances", "vis_pairs", "vis_any", "keys", "keys_alt", "final_T",
-        "n_contrib")]
+        "n_contrib", "cull", "color")]
 
 
 class EpipolarDesc(ctypes.Structure):

@@ -25,6 +25,14 @@ struct Geom {
     long long *n_instances;   // [0] instances, [1] longest segment, [2] #vis_pairs, [3] #vis_any
     uint32_t *vis_pairs;      // compact list of (view, Gaussian) flat indices that are on screen
     uint32_t *vis_any;        // compact list of (scene, Gaussian) flat indices visible in >= 1 view
+    float4 *cull;             // xy + half-extents of the alpha >= 1/255 box (compositor's cull record)
+};
+
+// Per-view image-space state kept from forward to backward.
+struct ImageState {
+    float *final_T;           // [S*V*H*W]
+    uint32_t *n_contrib;      // [S*V*H*W]
+    float *color;             // [S*V*3*H*W] copy of the rendered colour (backward's forward-order prefix form)
 };
 
 struct Dims {
@@ -42,6 +50,19 @@ struct ViewGrads {
     float4 *d_conic;   // x, y (half-weighted B), z, w = d_opacity
     float4 *d_color;   // r, g, b, unused
 };
+
+// Half-extents (pixels) of the axis-aligned box outside of which a splat's alpha is certainly
+// < 1/255: alpha = o exp(-0.5 d^T Sigma^-1 d) >= 1/255  <=>  d^T Sigma^-1 d <= 2 ln(255 o), whose bounding
+// box is sqrt(2 ln(255 o) Sigma_ii) -- taken from the 2D covariance itself (a, c = its diagonal), so no
+// cancellation; the margins cover the compositor's approximate exp2 and the rounding of the conic.
+// Large negative = never contributes; large positive = always evaluated (NaN inputs then propagate into
+// the image exactly as they would upstream).
+__device__ __forceinline__ float2 cull_extent(float a, float c, float o) {
+    if (!(a > 0.0f) || !(c > 0.0f) || !(o <= 3.0e38f)) return make_float2(3.0e38f, 3.0e38f);
+    if (!(o * 255.0f >= 1.0f - 1e-3f)) return make_float2(-3.0e38f, -3.0e38f);
+    const float tau2 = 2.0f * (__logf(fmaxf(o * 255.0f, 1.0f)) + 0.01f);
+    return make_float2(sqrtf(tau2 * a) * 1.001f + 0.01f, sqrtf(tau2 * c) * 1.001f + 0.01f);
+}
 
 void set_error(const char *fmt, ...);
 
@@ -88,12 +109,19 @@ int launch_sh_color(const Dims &d, const Inputs &in, const Geom &g, cudaStream_t
 int launch_binning(const Dims &d, const Geom &g, unsigned long long *keys,
                    unsigned long long *keys_alt, int sort_impl, int segment_hint, cudaStream_t st);
 int launch_composite_forward(const Dims &d, const Inputs &in, const Geom &g,
-                             const unsigned long long *keys, float *final_T, uint32_t *n_contrib,
+                             const unsigned long long *keys, const ImageState &img,
                              float *out_color, cudaStream_t st);
 int launch_composite_backward(const Dims &d, const Inputs &in, const Geom &g,
-                              const unsigned long long *keys, const float *final_T,
-                              const uint32_t *n_contrib, const float *d_color, const ViewGrads &vg,
-                              cudaStream_t st);
+                              const unsigned long long *keys, const ImageState &img,
+                              const float *d_color, const ViewGrads &vg, cudaStream_t st);
+// legacy CTA-per-tile compositor (round 1), kept selectable for A/B measurements
+int launch_composite_forward_v1(const Dims &d, const Inputs &in, const Geom &g,
+                                const unsigned long long *keys, const ImageState &img,
+                                float *out_color, cudaStream_t st);
+int launch_composite_backward_v1(const Dims &d, const Inputs &in, const Geom &g,
+                                 const unsigned long long *keys, const ImageState &img,
+                                 const float *d_color, const ViewGrads &vg, cudaStream_t st);
+int composite_impl();   // 1 = legacy, 2 = warp-task compositor (env PIXELSPLAT_B200_COMPOSITE, default 2)
 int launch_preprocess_backward(const Dims &d, const Inputs &in, const Geom &g, const ViewGrads &vg,
                                const ps_raster_grads &out, cudaStream_t st);
 int launch_gradient_fill(const Dims &d, const ps_raster_grads &out, cudaStream_t st);

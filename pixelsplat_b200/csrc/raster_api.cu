@@ -127,6 +127,7 @@ static Layout make_layout(const ps_raster_desc *d) {
     L.off.n_instances = take(32);   // [0] instances, [1] longest segment, [2] #visible pairs, [3] #visible Gaussians
     L.off.vis_pairs = take(vp * 4);
     L.off.vis_any = take((size_t)m.S * m.P * 4);
+    L.off.cull = take(vp * 16);
     L.sizes.geom_bytes = o;
     o = 0;
     L.off.keys = take((size_t)m.capacity * 8);
@@ -135,6 +136,7 @@ static Layout make_layout(const ps_raster_desc *d) {
     o = 0;
     L.off.final_T = take(px * 4);
     L.off.n_contrib = take(px * 4);
+    L.off.color = take(px * 12);
     L.sizes.image_bytes = o;
     // backward scratch: d_mean2d (8) + d_conic (16) + d_color (16) per (view, Gaussian)
     L.sizes.backward_bytes = align_up(vp * 8) + align_up(vp * 16) + align_up(vp * 16);
@@ -157,7 +159,17 @@ static Geom make_geom(const Layout &L, void *geom) {
     g.n_instances = reinterpret_cast<long long *>(b + L.off.n_instances);
     g.vis_pairs = reinterpret_cast<uint32_t *>(b + L.off.vis_pairs);
     g.vis_any = reinterpret_cast<uint32_t *>(b + L.off.vis_any);
+    g.cull = reinterpret_cast<float4 *>(b + L.off.cull);
     return g;
+}
+
+static ImageState make_image(const Layout &L, void *image) {
+    char *b = static_cast<char *>(image);
+    ImageState im;
+    im.final_T = reinterpret_cast<float *>(b + L.off.final_T);
+    im.n_contrib = reinterpret_cast<uint32_t *>(b + L.off.n_contrib);
+    im.color = reinterpret_cast<float *>(b + L.off.color);
+    return im;
 }
 
 static int check_common(const ps_raster_desc *desc, const ps_raster_inputs *in, const ps_raster_state *state,
@@ -249,8 +261,7 @@ PS_API int ps_raster_forward(const ps_raster_desc *desc, const ps_raster_inputs 
     const Geom g = make_geom(L, state->geom);
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(static_cast<char *>(state->binning) + L.off.keys);
     unsigned long long *keys_alt = reinterpret_cast<unsigned long long *>(static_cast<char *>(state->binning) + L.off.keys_alt);
-    float *final_T = reinterpret_cast<float *>(static_cast<char *>(state->image) + L.off.final_T);
-    uint32_t *n_contrib = reinterpret_cast<uint32_t *>(static_cast<char *>(state->image) + L.off.n_contrib);
+    const ImageState img = make_image(L, state->image);
 
     mark(kMarkFwdStart, st);
     SideCtx *sc = nullptr;
@@ -268,7 +279,7 @@ PS_API int ps_raster_forward(const ps_raster_desc *desc, const ps_raster_inputs 
     PS_CUDA_CHECK(cudaStreamWaitEvent(st, sc->join, 0));   // join
     if (n_instances_host)
         PS_CUDA_CHECK(cudaMemcpyAsync(n_instances_host, g.n_instances, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    if ((rc = launch_composite_forward(d, I, g, keys, final_T, n_contrib, out_color, st))) return rc;
+    if ((rc = launch_composite_forward(d, I, g, keys, img, out_color, st))) return rc;
     mark(kMarkCompositeFwd, st);
     if (out_radii)
         PS_CUDA_CHECK(cudaMemcpyAsync(out_radii, g.radii, sizeof(int32_t) * (size_t)d.S * d.V * d.P,
@@ -298,8 +309,7 @@ PS_API int ps_raster_backward(const ps_raster_desc *desc, const ps_raster_inputs
     const Inputs I = make_inputs(in);
     const Geom g = make_geom(L, state->geom);
     const unsigned long long *keys = reinterpret_cast<const unsigned long long *>(static_cast<char *>(state->binning) + L.off.keys);
-    const float *final_T = reinterpret_cast<const float *>(static_cast<char *>(state->image) + L.off.final_T);
-    const uint32_t *n_contrib = reinterpret_cast<const uint32_t *>(static_cast<char *>(state->image) + L.off.n_contrib);
+    const ImageState img = make_image(L, state->image);
     const size_t vp = (size_t)d.S * d.V * d.P;
     char *sb = static_cast<char *>(scratch);
     ViewGrads vg;
@@ -316,7 +326,7 @@ PS_API int ps_raster_backward(const ps_raster_desc *desc, const ps_raster_inputs
     PS_CUDA_CHECK(cudaEventRecord(sc->join, sc->side));
     PS_CUDA_CHECK(cudaMemsetAsync(scratch, 0, L.sizes.backward_bytes, st));
     mark(kMarkBwdZero, st);
-    if ((rc = launch_composite_backward(d, I, g, keys, final_T, n_contrib, d_color, vg, st))) return rc;
+    if ((rc = launch_composite_backward(d, I, g, keys, img, d_color, vg, st))) return rc;
     mark(kMarkCompositeBwd, st);
     PS_CUDA_CHECK(cudaStreamWaitEvent(st, sc->join, 0));   // join
     if ((rc = launch_preprocess_backward(d, I, g, vg, *grads, st))) return rc;

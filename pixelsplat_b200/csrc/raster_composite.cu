@@ -1,3 +1,5 @@
+// LEGACY (round-1) compositor, selectable with PIXELSPLAT_B200_COMPOSITE=1 for A/B measurements; the
+// default is the warp-task compositor in raster_composite2.cu.
 // Alpha compositing, forward (front-to-back) and backward (back-to-front).
 // One CTA per (view, 16x16 tile); each warp owns an 8x4 pixel sub-rectangle, each lane a pixel.
 // The tile's sorted instance list is staged 256 entries at a time in shared memory.
@@ -122,7 +124,8 @@ __device__ __forceinline__ void take4(HitCarry &c, uint32_t &mask, uint32_t jb, 
 __global__ void __launch_bounds__(kCompThreads)
 k_composite_fwd(Dims d, Geom geo, const float *__restrict__ bg_all,
                 const unsigned long long *__restrict__ keys, float *__restrict__ final_T,
-                uint32_t *__restrict__ n_contrib, float *__restrict__ out_color) {
+                uint32_t *__restrict__ n_contrib, float *__restrict__ state_color,
+                float *__restrict__ out_color) {
     __shared__ StageBuf s;
     const int vid = blockIdx.y, tile = blockIdx.x;
     const int tx = tile % d.gx, ty = tile / d.gx;
@@ -210,9 +213,10 @@ k_composite_fwd(Dims d, Geom geo, const float *__restrict__ bg_all,
         n_contrib[(size_t)vid * hw + pix] = last;
         const float *bg = bg_all + 3 * vid;
         float *o = out_color + (size_t)vid * 3 * hw;
-        o[pix] = Cr + T * bg[0];
-        o[hw + pix] = Cg + T * bg[1];
-        o[2 * hw + pix] = Cb + T * bg[2];
+        float *sc = state_color + (size_t)vid * 3 * hw;
+        sc[pix] = o[pix] = Cr + T * bg[0];
+        sc[hw + pix] = o[hw + pix] = Cg + T * bg[1];
+        sc[2 * hw + pix] = o[2 * hw + pix] = Cb + T * bg[2];
     }
 }
 
@@ -520,19 +524,20 @@ k_composite_bwd(Dims d, Geom geo, const float *__restrict__ bg_all,
     }
 }
 
-int launch_composite_forward(const Dims &d, const Inputs &in, const Geom &g,
-                             const unsigned long long *keys, float *final_T, uint32_t *n_contrib,
-                             float *out_color, cudaStream_t st) {
+int launch_composite_forward_v1(const Dims &d, const Inputs &in, const Geom &g,
+                                const unsigned long long *keys, const ImageState &img,
+                                float *out_color, cudaStream_t st) {
     dim3 grid(d.tiles, d.S * d.V);
-    k_composite_fwd<<<grid, kCompThreads, 0, st>>>(d, g, in.bg, keys, final_T, n_contrib, out_color);
+    k_composite_fwd<<<grid, kCompThreads, 0, st>>>(d, g, in.bg, keys, img.final_T, img.n_contrib, img.color, out_color);
     PS_LAUNCH_CHECK("k_composite_fwd");
     return PS_OK;
 }
 
-int launch_composite_backward(const Dims &d, const Inputs &in, const Geom &g,
-                              const unsigned long long *keys, const float *final_T,
-                              const uint32_t *n_contrib, const float *d_color, const ViewGrads &vg,
-                              cudaStream_t st) {
+int launch_composite_backward_v1(const Dims &d, const Inputs &in, const Geom &g,
+                                 const unsigned long long *keys, const ImageState &img,
+                                 const float *d_color, const ViewGrads &vg, cudaStream_t st) {
+    const float *final_T = img.final_T;
+    const uint32_t *n_contrib = img.n_contrib;
     dim3 grid(d.tiles, d.S * d.V);
     const size_t acc_bytes = sizeof(float) * (kCompThreads / 32) * kStage * 10;
     static unsigned long long attr_devices = 0;

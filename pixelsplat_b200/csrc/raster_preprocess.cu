@@ -115,6 +115,10 @@ k_preprocess(Dims d, Inputs in, Geom geo, int use_smem_hist) {
                     geo.radii[vg] = r;
                     geo.xy[vg] = make_float2(pixx, pixy);
                     geo.conic_opacity[vg] = make_float4(cv.c * det_inv, -cv.b * det_inv, cv.a * det_inv, opacity);
+                    {
+                        const float2 ext = cull_extent(cv.a, cv.c, opacity);
+                        geo.cull[vg] = make_float4(pixx, pixy, ext.x, ext.y);
+                    }
                     geo.rect[vg] = make_ushort4((unsigned short)minx, (unsigned short)miny,
                                                 (unsigned short)maxx, (unsigned short)maxy);
                     if (d.M == 0) {
