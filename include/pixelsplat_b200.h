@@ -46,6 +46,14 @@ extern "C" {
 /* sh_layout */
 #define PS_SH_M3 0 /* [P, M, 3]  what GaussianRasterizer.forward receives (cuda_splatting.py:75) */
 #define PS_SH_3M 1 /* [P, 3, M]  pixelSplat's native Gaussians.harmonics (model/types.py:11)    */
+/* SH convention (ps_raster_desc.sh_basis, ps_sh_rotation_matrices' `convention`):
+ *   3DGS  z polar, Condon-Shortley sign (-1)^m, degree 1 = C1 (-y, z, -x): upstream 3DGS;
+ *   E3NN  y polar, no Condon-Shortley sign, degree 1 = C1 (x, y, z): the basis of e3nn's real harmonics,
+ *         in which the reference rotates its coefficients (/root/reference/src/misc/sh_rotation.py:18-22,
+ *         ply_export.py:75 "our axes are swizzled for the spherical harmonics").
+ *   Y_e3nn,i(x, y, z) = (-1)^m Y_3dgs,i(z, x, y). */
+#define PS_SH_BASIS_3DGS 0
+#define PS_SH_BASIS_E3NN 1
 /* cov_layout */
 #define PS_COV_TRIU6 0 /* [P, 6]  xx,xy,xz,yy,yz,zz = cov3D_precomp (cuda_splatting.py:115,123) */
 #define PS_COV_3X3 1   /* [P, 3, 3]  Gaussians.covariances; only the upper triangle is read, and
@@ -65,6 +73,9 @@ typedef struct ps_raster_desc {
                                   n_instances_host[1]); 0 = unknown.  Only selects the shared-memory
                                   size of the sort; any value is correct                        */
     int64_t instance_capacity; /* room, in (tile,Gaussian) instances, summed over all S*V views */
+    /* appended in round 2 (struct grows at the end only) */
+    int32_t sh_basis;        /* PS_SH_BASIS_*: the convention the SH coefficients are evaluated in    */
+    int32_t reserved;        /* must be 0                                                      */
 } ps_raster_desc;
 
 /* Per-call inputs. Camera arrays are indexed by flat view id  vid = scene * V + view. */
@@ -296,11 +307,14 @@ PS_API int ps_gaussian_adapter_backward(const ps_adapter_desc *desc, const ps_ad
 
 /* Block-diagonal SH rotation matrices D(c2w) [n_views, sh_coeffs, sh_coeffs] for ps_adapter_inputs.sh_rotation
  * (replaces /root/reference/src/misc/sh_rotation.py:10-30, row f-3): c' = D c makes the rotated function at
- * d equal the original at R^T d, in the basis the rasterizer evaluates.  fit_dirs [n_dirs, 3] are unit
- * directions and fit_pinv [sh_coeffs, n_dirs] the per-degree pseudo-inverse of the basis sampled there
- * (pixelsplat_b200/sh.py builds both once, in float64).  extrinsics [n_views, 4, 4] camera-to-world. */
-PS_API int ps_sh_rotation_matrices(int32_t n_views, int32_t sh_coeffs, int32_t n_dirs, const float *extrinsics,
-                                   const float *fit_dirs, const float *fit_pinv, float *out, void *stream);
+ * d equal the original at R^T d, in the basis `convention` names.  PS_SH_BASIS_E3NN reproduces the reference's
+ * wigner_D(l, *matrix_to_angles(R)) (degree-1 block == R); PS_SH_BASIS_3DGS is the rotation consistent with the
+ * rasterizer's default basis.  fit_dirs [n_dirs, 3] are unit directions and fit_pinv [sh_coeffs, n_dirs] the
+ * per-degree pseudo-inverse of the 3DGS basis sampled there (pixelsplat_b200/sh.py builds both once, in
+ * float64).  extrinsics [n_views, 4, 4] camera-to-world. */
+PS_API int ps_sh_rotation_matrices(int32_t n_views, int32_t sh_coeffs, int32_t n_dirs, int32_t convention,
+                                   const float *extrinsics, const float *fit_dirs, const float *fit_pinv,
+                                   float *out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -4,11 +4,14 @@ container only:
 
     python oracle/make_adapter_golden.py
 
-TEST INFRASTRUCTURE.  The reference's `rotate_sh` needs e3nn (absent offline), so the adapter is run
-with `rotate_sh` replaced by the identity: the fixture pins everything except the SH rotation
-(means, covariances, scales, rotations, opacities, masked + broadcast harmonics, and the gradients
-of tests/golden_util.adapter_loss).  Inputs and weights are regenerated from tests/golden_util.py
-on both sides; only reference outputs are stored.
+TEST INFRASTRUCTURE.  The reference's `rotate_sh` (src/misc/sh_rotation.py:10-30) is two e3nn calls
+and e3nn is absent offline, so the reference module runs with its `rotate_sh` bound to
+oracle/wigner_e3nn.rotate_sh_reference -- the same function body on a restatement of e3nn's published
+`matrix_to_angles` / `wigner_D` (float64 generators; see that file for how it is pinned).  Everything
+else is the reference's own code: means, covariances, scales, rotations, opacities, masked + broadcast +
+ROTATED harmonics, and the gradients of tests/golden_util.adapter_loss.  Inputs and weights are
+regenerated from tests/golden_util.py on both sides; only reference outputs are stored.
+(adapter_v1.npz, round 1, had the rotation replaced by the identity.)
 """
 from __future__ import annotations
 
@@ -20,7 +23,7 @@ import torch
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
-from oracle import epipolar_ref  # noqa: E402
+from oracle import epipolar_ref, wigner_e3nn  # noqa: E402
 from tests import golden_util as gu  # noqa: E402
 
 OUT = ROOT / "tests" / "golden"
@@ -69,7 +72,7 @@ def depth_predictor(ns, dtype, tag, out):
 
 def main():
     ns = epipolar_ref.load_adapter()
-    ns.module.rotate_sh = lambda sh, rotations: sh                    # see the module docstring
+    ns.module.rotate_sh = wigner_e3nn.rotate_sh_reference             # see the module docstring
     # the reference hard-codes a float32 pixel_size (gaussian_adapter.py:68); cast it so the module also
     # runs in float64 (value-preserving: 1/w and 1/h are first formed in float32 exactly as upstream)
     orig = ns.GaussianAdapter.get_scale_multiplier
@@ -84,8 +87,8 @@ def main():
         finally:
             torch.set_default_dtype(torch.float32)
     OUT.mkdir(parents=True, exist_ok=True)
-    np.savez_compressed(OUT / "adapter_v1.npz", **out)
-    print("wrote", OUT / "adapter_v1.npz", {k: v.shape for k, v in list(out.items())[:8]}, len(out), "arrays")
+    np.savez_compressed(OUT / "adapter_v2.npz", **out)
+    print("wrote", OUT / "adapter_v2.npz", {k: v.shape for k, v in list(out.items())[:8]}, len(out), "arrays")
 
 
 if __name__ == "__main__":

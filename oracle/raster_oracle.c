@@ -68,7 +68,7 @@ static inline int imax(int a, int b) { return a > b ? a : b; }
 int orc_real_bytes(void) { return (int)sizeof(real); }
 
 /* Real-SH basis, degrees 0..4, 3DGS sign convention. */
-static void sh_basis(int deg, real x, real y, real z, real *b) {
+static void sh_basis_3dgs(int deg, real x, real y, real z, real *b) {
     b[0] = K(SH_C0);
     if (deg < 1) return;
     b[1] = -K(SH_C1) * y;
@@ -103,7 +103,7 @@ static void sh_basis(int deg, real x, real y, real z, real *b) {
 
 /* d basis / d (x,y,z), treating x,y,z as independent (the normalisation
  * Jacobian is applied by the caller). */
-static void sh_basis_grad(int deg, real x, real y, real z, real *dx, real *dy, real *dz) {
+static void sh_basis_grad_3dgs(int deg, real x, real y, real z, real *dx, real *dy, real *dz) {
     for (int i = 0; i < 25; ++i) dx[i] = dy[i] = dz[i] = 0;
     if (deg < 1) return;
     dy[1] = -K(SH_C1);
@@ -143,6 +143,25 @@ static void sh_basis_grad(int deg, real x, real y, real z, real *dx, real *dy, r
     dx[23] = K(SH_C4[7]) * z * (K(3) * xx - K(3) * yy);  dy[23] = K(SH_C4[7]) * K(-6) * xy * z;  dz[23] = K(SH_C4[7]) * x * (xx - K(3) * yy);
     /* b24 = c (x^4 - 6 x^2 y^2 + y^4) */
     dx[24] = K(SH_C4[8]) * (K(4) * xx * x - K(12) * x * yy);  dy[24] = K(SH_C4[8]) * (K(4) * yy * y - K(12) * xx * y);
+}
+
+/* SH convention switch (include/pixelsplat_b200.h PS_SH_BASIS_*): 0 = 3DGS (default), 1 = e3nn, the
+ * basis in which the reference rotates its coefficients (src/misc/sh_rotation.py:18-22):
+ *   Y_e3nn,k(x, y, z) = (-1)^m Y_3dgs,k(z, x, y),  and (-1)^m = (-1)^k because l^2 + l is even. */
+static int g_sh_convention = 0;
+void orc_set_sh_basis(int convention) { g_sh_convention = convention; }
+
+static void sh_basis(int deg, real x, real y, real z, real *b) {
+    if (g_sh_convention == 0) { sh_basis_3dgs(deg, x, y, z, b); return; }
+    sh_basis_3dgs(deg, z, x, y, b);
+    for (int k = 1; k < (deg + 1) * (deg + 1); k += 2) b[k] = -b[k];
+}
+
+static void sh_basis_grad(int deg, real x, real y, real z, real *dx, real *dy, real *dz) {
+    if (g_sh_convention == 0) { sh_basis_grad_3dgs(deg, x, y, z, dx, dy, dz); return; }
+    /* f(x, y, z) = g(a, b, c) at (a, b, c) = (z, x, y): df/dx = dg/db, df/dy = dg/dc, df/dz = dg/da */
+    sh_basis_grad_3dgs(deg, z, x, y, dz, dx, dy);
+    for (int k = 1; k < 25; k += 2) { dx[k] = -dx[k]; dy[k] = -dy[k]; dz[k] = -dz[k]; }
 }
 
 typedef struct {

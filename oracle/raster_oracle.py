@@ -44,6 +44,28 @@ def _lib(dtype) -> ctypes.CDLL:
     return _LIBS[name]
 
 
+class sh_basis:
+    """Context manager: evaluate SH in the given convention (0 = 3DGS default, 1 = e3nn) in the C oracle
+    (both precisions) and in raster_torch for the duration of the block."""
+
+    def __init__(self, convention: int):
+        self.convention = int(convention)
+
+    def _set(self, c: int) -> None:
+        from . import raster_torch
+        for dt in (np.float32, np.float64):
+            _lib(dt).orc_set_sh_basis(ctypes.c_int(c))
+        raster_torch.set_sh_basis(c)
+
+    def __enter__(self):
+        self._set(self.convention)
+        return self
+
+    def __exit__(self, *exc):
+        self._set(0)
+        return False
+
+
 def _p(a: np.ndarray | None):
     if a is None:
         return None

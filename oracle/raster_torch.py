@@ -30,8 +30,26 @@ SH_C4 = [2.5033429417967046, -1.7701307697799304, 0.9461746957575601, -0.6690465
          0.6258357354491761]
 
 
+SH_CONVENTION = 0   # 0 = 3DGS basis (default), 1 = e3nn basis (include/pixelsplat_b200.h PS_SH_BASIS_*)
+
+
+def set_sh_basis(convention: int) -> None:
+    global SH_CONVENTION
+    SH_CONVENTION = int(convention)
+
+
 def sh_basis(deg: int, d: torch.Tensor) -> torch.Tensor:
-    """d: [P,3] unit vectors -> [P,(deg+1)^2]."""
+    """d: [P,3] unit vectors -> [P,(deg+1)^2].  With SH_CONVENTION = 1 the e3nn basis:
+    Y_e3nn,k(x, y, z) = (-1)^k Y_3dgs,k(z, x, y) (the basis the reference's rotate_sh rotates in,
+    /root/reference/src/misc/sh_rotation.py:18-22)."""
+    if SH_CONVENTION == 1:
+        x, y, z = d.unbind(-1)
+        sign = torch.tensor([(-1.0) ** k for k in range((deg + 1) ** 2)], dtype=d.dtype, device=d.device)
+        return _sh_basis_3dgs(deg, torch.stack([z, x, y], dim=-1)) * sign
+    return _sh_basis_3dgs(deg, d)
+
+
+def _sh_basis_3dgs(deg: int, d: torch.Tensor) -> torch.Tensor:
     x, y, z = d.unbind(-1)
     b = [torch.full_like(x, SH_C0)]
     if deg >= 1:

@@ -15,6 +15,7 @@ LIB_PATH = Path(os.environ.get("PIXELSPLAT_B200_LIB", _PKG / "_C" / "libpixelspl
 PS_OK = 0
 PS_SH_M3, PS_SH_3M = 0, 1
 PS_COV_TRIU6, PS_COV_3X3 = 0, 1
+PS_SH_BASIS_3DGS, PS_SH_BASIS_E3NN = 0, 1
 TILE = 16
 
 _ERR_NAMES = {1: "PS_ERR_INVALID_ARGUMENT", 2: "PS_ERR_CUDA", 3: "PS_ERR_UNSUPPORTED"}
@@ -28,6 +29,7 @@ class RasterDesc(ctypes.Structure):
         ("cov_layout", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
         ("sort_impl", ctypes.c_int32), ("sort_segment_hint", ctypes.c_int32),
         ("instance_capacity", ctypes.c_int64),
+        ("sh_basis", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]
 
 
@@ -130,7 +132,7 @@ def _load() -> ctypes.CDLL:
     lib.ps_gaussian_adapter_forward.restype = ctypes.c_int
     lib.ps_gaussian_adapter_backward.argtypes = [P(AdapterDesc), P(AdapterInputs)] + [ctypes.c_void_p] * 9
     lib.ps_gaussian_adapter_backward.restype = ctypes.c_int
-    lib.ps_sh_rotation_matrices.argtypes = [ctypes.c_int32] * 3 + [ctypes.c_void_p] * 5
+    lib.ps_sh_rotation_matrices.argtypes = [ctypes.c_int32] * 4 + [ctypes.c_void_p] * 5
     lib.ps_sh_rotation_matrices.restype = ctypes.c_int
     for f in ("ps_raster_sizes_query", "ps_raster_layout_query", "ps_raster_forward", "ps_raster_backward"):
         getattr(lib, f).restype = ctypes.c_int

@@ -373,11 +373,15 @@ k_gaussian_adapter_bwd(ps_adapter_desc d, ps_adapter_inputs in, const float *__r
 }
 
 // D(R) for every camera: c' = D c  <=>  sum_i c'_i Y_i(d) = sum_i c_i Y_i(R^T d).  Y+ (the per-degree
-// pseudo-inverse of the basis sampled at `m` fixed directions, float64-fitted on the host once) turns
+// pseudo-inverse of the 3DGS basis sampled at `m` fixed directions, float64-fitted on the host once) turns
 // the basis values at the rotated directions into the block-diagonal matrix: D_l = Y+_l Y_l(R^T d).
 // One CTA per camera; the dot products accumulate in double (m = 192 terms).
+// convention PS_SH_BASIS_E3NN (what the reference's rotate_sh computes, sh_rotation.py:18-22): e3nn's
+// harmonics are Y_e,i(x, y, z) = s_i Y_3dgs,i(z, x, y), s_i = (-1)^m, hence
+// D_e3nn(R) = S D_3dgs(Q R Q^T) S with Q the axis permutation (x, y, z) -> (z, x, y): the same fit on the
+// permuted rotation, then a sign per entry.
 __global__ void __launch_bounds__(256)
-k_sh_rotation(int n_sh, int m, const float *__restrict__ extrinsics, const float *__restrict__ dirs,
+k_sh_rotation(int n_sh, int m, int convention, const float *__restrict__ extrinsics, const float *__restrict__ dirs,
               const float *__restrict__ pinv, float *__restrict__ out) {
     extern __shared__ float s_y[];                    // [m][n_sh] basis at R^T d, then [n_sh][m] pinv
     float *s_pinv = s_y + (size_t)m * n_sh;
@@ -387,9 +391,17 @@ k_sh_rotation(int n_sh, int m, const float *__restrict__ extrinsics, const float
     for (int e = tid; e < n_sh * m; e += blockDim.x) s_pinv[e] = pinv[e];
     for (int t = tid; t < m; t += blockDim.x) {
         const float dx = dirs[3 * t], dy = dirs[3 * t + 1], dz = dirs[3 * t + 2];
-        const float x = E[0] * dx + E[4] * dy + E[8] * dz;          // R^T d  (R = E[:3,:3], row-major, stride 4)
-        const float y = E[1] * dx + E[5] * dy + E[9] * dz;
-        const float z = E[2] * dx + E[6] * dy + E[10] * dz;
+        float x, y, z;
+        if (convention == PS_SH_BASIS_E3NN) {
+            // R' = Q R Q^T, R'[a][b] = R[p(a)][p(b)], p = (2, 0, 1);  (R'^T d)_b = sum_a R[p(a)][p(b)] d_a
+            x = E[4 * 2 + 2] * dx + E[4 * 0 + 2] * dy + E[4 * 1 + 2] * dz;
+            y = E[4 * 2 + 0] * dx + E[4 * 0 + 0] * dy + E[4 * 1 + 0] * dz;
+            z = E[4 * 2 + 1] * dx + E[4 * 0 + 1] * dy + E[4 * 1 + 1] * dz;
+        } else {
+            x = E[0] * dx + E[4] * dy + E[8] * dz;                   // R^T d  (R = E[:3,:3], row-major, stride 4)
+            y = E[1] * dx + E[5] * dy + E[9] * dz;
+            z = E[2] * dx + E[6] * dy + E[10] * dz;
+        }
         float *row = s_y + (size_t)t * n_sh;
         sh_for_each(deg, x, y, z, [&](int i, float v, float, float, float) { row[i] = v; });
     }
@@ -411,7 +423,10 @@ k_sh_rotation(int n_sh, int m, const float *__restrict__ extrinsics, const float
             }
             for (; t < m; ++t) a0 += (double)pr[t] * (double)yc[(size_t)t * n_sh];
         }
-        out[(size_t)view * n_sh * n_sh + e] = (float)((a0 + a1) + (a2 + a3));
+        float v = (float)((a0 + a1) + (a2 + a3));
+        // (-1)^(m_i + m_j), m = index - l^2 - l: same degree => parity of (i - j)
+        if (convention == PS_SH_BASIS_E3NN && ((i - j) & 1)) v = -v;
+        out[(size_t)view * n_sh * n_sh + e] = v;
     }
 }
 
@@ -482,12 +497,16 @@ extern "C" PS_API int ps_gaussian_adapter_backward(const ps_adapter_desc *desc, 
     return PS_OK;
 }
 
-extern "C" PS_API int ps_sh_rotation_matrices(int32_t n_views, int32_t sh_coeffs, int32_t n_dirs,
+extern "C" PS_API int ps_sh_rotation_matrices(int32_t n_views, int32_t sh_coeffs, int32_t n_dirs, int32_t convention,
                                               const float *extrinsics, const float *fit_dirs,
                                               const float *fit_pinv, float *out, void *stream) {
     using namespace ps;
     if (n_views < 1 || n_dirs < 1 || n_dirs > 512 || !extrinsics || !fit_dirs || !fit_pinv || !out) {
         set_error("ps_sh_rotation_matrices: bad argument");
+        return PS_ERR_INVALID_ARGUMENT;
+    }
+    if (convention != PS_SH_BASIS_3DGS && convention != PS_SH_BASIS_E3NN) {
+        set_error("ps_sh_rotation_matrices: convention must be PS_SH_BASIS_3DGS or PS_SH_BASIS_E3NN (got %d)", convention);
         return PS_ERR_INVALID_ARGUMENT;
     }
     if (sh_coeffs != 1 && sh_coeffs != 4 && sh_coeffs != 9 && sh_coeffs != 16 && sh_coeffs != 25) {
@@ -499,7 +518,7 @@ extern "C" PS_API int ps_sh_rotation_matrices(int32_t n_views, int32_t sh_coeffs
         PS_CUDA_CHECK(cudaFuncSetAttribute(k_sh_rotation, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     }
     k_sh_rotation<<<n_views, 256, 2 * sizeof(float) * n_dirs * sh_coeffs, static_cast<cudaStream_t>(stream)>>>(
-        sh_coeffs, n_dirs, extrinsics, fit_dirs, fit_pinv, out);
+        sh_coeffs, n_dirs, convention, extrinsics, fit_dirs, fit_pinv, out);
     PS_LAUNCH_CHECK("k_sh_rotation");
     return PS_OK;
 }

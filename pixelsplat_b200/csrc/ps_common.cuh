@@ -36,7 +36,7 @@ struct ImageState {
 };
 
 struct Dims {
-    int S, V, P, M, deg, sh_layout, cov_layout, H, W, gx, gy, tiles;
+    int S, V, P, M, deg, sh_layout, cov_layout, H, W, gx, gy, tiles, sh_basis;
     long long capacity;
 };
 

@@ -76,6 +76,8 @@ static int validate(const ps_raster_desc *d) {
         return PS_ERR_INVALID_ARGUMENT;
     }
     if (d->sh_layout != PS_SH_M3 && d->sh_layout != PS_SH_3M) { set_error("bad sh_layout %d", d->sh_layout); return PS_ERR_INVALID_ARGUMENT; }
+    if (d->sh_basis != PS_SH_BASIS_3DGS && d->sh_basis != PS_SH_BASIS_E3NN) { set_error("bad sh_basis %d", d->sh_basis); return PS_ERR_INVALID_ARGUMENT; }
+    if (d->reserved != 0) { set_error("ps_raster_desc.reserved must be 0 (got %d): caller built against an older header?", d->reserved); return PS_ERR_INVALID_ARGUMENT; }
     if (d->cov_layout != PS_COV_TRIU6 && d->cov_layout != PS_COV_3X3) { set_error("bad cov_layout %d", d->cov_layout); return PS_ERR_INVALID_ARGUMENT; }
     if (d->instance_capacity < 1 || d->instance_capacity > 0x7fffffffll) {
         set_error("instance_capacity must be in [1, 2^31-1], got %lld", (long long)d->instance_capacity);
@@ -103,6 +105,7 @@ static Dims make_dims(const ps_raster_desc *d) {
     r.gx = (d->width + kTile - 1) / kTile; r.gy = (d->height + kTile - 1) / kTile;
     r.tiles = r.gx * r.gy;
     r.capacity = d->instance_capacity;
+    r.sh_basis = d->sh_basis;
     return r;
 }
 

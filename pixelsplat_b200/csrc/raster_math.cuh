@@ -125,6 +125,23 @@ __device__ __forceinline__ void sh_for_each(int deg, float x, float y, float z, 
     }
 }
 
+// The e3nn convention (PS_SH_BASIS_E3NN) on top of the same polynomials:
+//   Y_e3nn,k(x, y, z) = (-1)^m Y_k(z, x, y), and (-1)^m = (-1)^k because l^2 + l is even.
+// Callers evaluate sh_for_each at sh_arg(basis, x, y, z), flip the sign of odd-k terms with sh_sign()
+// (an exact operation: results stay bit-identical to the oracle's), and map the derivative triple back
+// with sh_grad_unpermute().  k is a literal at every call site of the visitor, so `k & 1` folds away.
+__device__ __forceinline__ float3 sh_arg(int basis, float x, float y, float z) {
+    return basis == PS_SH_BASIS_E3NN ? make_float3(z, x, y) : make_float3(x, y, z);
+}
+__device__ __forceinline__ float sh_sign(uint32_t flip_mask, int k, float v) {
+    return (k & 1) ? __uint_as_float(__float_as_uint(v) ^ flip_mask) : v;
+}
+__device__ __forceinline__ uint32_t sh_flip_mask(int basis) { return basis == PS_SH_BASIS_E3NN ? 0x80000000u : 0u; }
+// f(x, y, z) = g(a, b, c) at (a, b, c) = (z, x, y):  df/dx = dg/db, df/dy = dg/dc, df/dz = dg/da
+__device__ __forceinline__ float3 sh_grad_unpermute(int basis, float da, float db, float dc) {
+    return basis == PS_SH_BASIS_E3NN ? make_float3(db, dc, da) : make_float3(da, db, dc);
+}
+
 // Cooperative, coalesced copy of one warp's 32 consecutive SH rows (3M floats each) from global
 // to shared memory (row stride padded to an odd word count -> the per-lane row reads that follow
 // are bank-conflict free).  A per-lane `__ldg(sh + k)` walk instead costs 32 L1 wavefronts per

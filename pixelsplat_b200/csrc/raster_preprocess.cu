@@ -182,7 +182,10 @@ k_sh_color(Dims d, Inputs in, Geom geo, int row_stride) {
     const float *row = wrows + lane * row_stride;
     float acc[3] = {0.0f, 0.0f, 0.0f};
     const int M = d.M, layout = d.sh_layout;
-    sh_for_each(d.deg, x, y, z, [&](int k, float Y, float, float, float) {
+    const float3 sa = sh_arg(d.sh_basis, x, y, z);
+    const uint32_t flip = sh_flip_mask(d.sh_basis);
+    sh_for_each(d.deg, sa.x, sa.y, sa.z, [&](int k, float Yk, float, float, float) {
+        const float Y = sh_sign(flip, k, Yk);
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
             const float c = row[sh_index(layout, M, k, ch)];

@@ -139,19 +139,24 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
             const float x = ddx / len, y = ddy / len, z = ddz / len;
             const uint8_t cl = geo.clamped[vg];
             const float dl[3] = {(cl & 1) ? 0.0f : gcol.x, (cl & 2) ? 0.0f : gcol.y, (cl & 4) ? 0.0f : gcol.z};
-            float dLdx = 0.0f, dLdy = 0.0f, dLdz = 0.0f;
+            float dLda = 0.0f, dLdb = 0.0f, dLdc = 0.0f;
             const bool first = !sh_written;
-            sh_for_each(d.deg, x, y, z, [&](int k, float Y, float Yx, float Yy, float Yz) {
+            const float3 sa = sh_arg(d.sh_basis, x, y, z);
+            const uint32_t flip = sh_flip_mask(d.sh_basis);
+            sh_for_each(d.deg, sa.x, sa.y, sa.z, [&](int k, float Y, float Ya, float Yb, float Yc) {
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
                     const int idx = sh_index(layout, M, k, ch);
                     const float coef = row[idx];
-                    const float val = Y * dl[ch];
+                    const float sdl = sh_sign(flip, k, dl[ch]);      // the term's sign rides on dL/dcolour
+                    const float val = Y * sdl;
                     grow[idx] = first ? val : grow[idx] + val;
-                    const float cd = coef * dl[ch];
-                    dLdx += Yx * cd; dLdy += Yy * cd; dLdz += Yz * cd;
+                    const float cd = coef * sdl;
+                    dLda += Ya * cd; dLdb += Yb * cd; dLdc += Yc * cd;
                 }
             });
+            const float3 dLd = sh_grad_unpermute(d.sh_basis, dLda, dLdb, dLdc);
+            const float dLdx = dLd.x, dLdy = dLd.y, dLdz = dLd.z;
             if (first) {
                 const int nb = (d.deg + 1) * (d.deg + 1);
                 for (int k = nb; k < M; ++k)

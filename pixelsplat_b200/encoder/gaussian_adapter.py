@@ -4,8 +4,11 @@ reference's ~40 element-wise / tiny-matmul torch kernels.
 
 Reference: /root/reference/src/model/encoder/common/gaussian_adapter.py:13-123 (same dataclasses,
 constructor, `forward` signature, `get_scale_multiplier`, `d_sh`, `d_in`, non-persistent `sh_mask`
-buffer) and gaussians.py:8-44.  The spherical-harmonics rotation uses pixelsplat_b200.sh (the
-reference calls e3nn, absent offline -- see that module's docstring for what is and is not pinned).
+buffer) and gaussians.py:8-44.  The spherical-harmonics rotation (gaussian_adapter.py:84,
+`rotate_sh` = e3nn Wigner-D of the camera-to-world rotation) uses pixelsplat_b200.sh, whose default
+convention "e3nn" reproduces the reference's matrices; `sh_rotation_convention = "3dgs"` (attribute of
+the module, not of the reference's cfg dataclass) opts into the rotation that is physically consistent
+with the rasterizer's default basis instead.
 
 The fused path covers the call shape EncoderEpipolar uses (encoder_epipolar.py:169-177): batch
 dims (b, v, r, srf, spp) with extrinsics / intrinsics constant over (r, srf, spp) and coordinates /
@@ -118,6 +121,7 @@ class _GaussianAdapterFn(torch.autograd.Function):
 
 class GaussianAdapter(nn.Module):
     cfg: GaussianAdapterCfg
+    sh_rotation_convention: str = "e3nn"     # the reference's rotate_sh; "3dgs" = rasterizer-consistent (opt-in)
 
     def __init__(self, cfg: GaussianAdapterCfg):
         super().__init__()
@@ -155,7 +159,7 @@ class GaussianAdapter(nn.Module):
         nv, nr = b * v, r * srf
         E = extrinsics.expand(b, v, 1, 1, 1, 4, 4).reshape(nv, 4, 4)
         K = intrinsics.expand(b, v, 1, 1, 1, 3, 3).reshape(nv, 3, 3)
-        D = camera_sh_rotations(E, self.cfg.sh_degree)
+        D = camera_sh_rotations(E, self.cfg.sh_degree, self.sh_rotation_convention)
         coords = coordinates.expand(b, v, r, srf, 1, 2).reshape(nv, nr, 2)
         means, cov, harm, scales, rot = _GaussianAdapterFn.apply(
             E.detach(), K.detach(), D, self.sh_mask, coords, depths.reshape(nv, nr, spp),
@@ -187,7 +191,8 @@ class GaussianAdapter(nn.Module):
         origins, directions = world_rays(coordinates, extrinsics, intrinsics)
         means = origins + directions * depths[..., None]
         return Gaussians(means=means, covariances=covariances,
-                         harmonics=rotate_sh(sh, c2w[..., None, :, :]) if rotate else sh,
+                         harmonics=(rotate_sh(sh, c2w[..., None, :, :], self.sh_rotation_convention)
+                                    if rotate else sh),
                          opacities=opacities, scales=scales,
                          rotations=rotations.broadcast_to((*scales.shape[:-1], 4)))
 

@@ -10,6 +10,8 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
+import weakref
 from typing import NamedTuple, Optional
 
 import torch
@@ -17,6 +19,7 @@ from torch import Tensor
 
 from . import _lib
 from ._lib import PS_COV_3X3, PS_COV_TRIU6, PS_SH_M3, TILE
+from .sh import convention_id
 
 # ------------------------------------------------------------------ instance-capacity policy
 # The binning buffers are sized for `capacity` (tile, Gaussian) instances.  The exact count is
@@ -24,14 +27,26 @@ from ._lib import PS_COV_3X3, PS_COV_TRIU6, PS_SH_M3, TILE
 #   "sync"     (default): wait for the count right after enqueueing the forward (one event wait
 #              per *batch* of views -- upstream syncs once per view) and transparently re-run with
 #              a larger buffer if it overflowed.  Always correct.
-#   "deferred": never block in forward; the count is verified when backward starts (or on the
-#              next forward of the same shape) and a RuntimeError is raised if it had overflowed.
+#   "deferred": a forward that will be followed by a backward (grad enabled, an input requires grad)
+#              does not block; its count is verified when its backward starts AND at the start of the
+#              next forward of the same shape, whichever comes first, and a RuntimeError is raised
+#              if it had overflowed.  Forwards with no backward coming (inference) are always checked
+#              synchronously, so a truncated image is never returned silently.
 _CHECK_MODE = os.environ.get("PIXELSPLAT_B200_CAPACITY_CHECK", "sync")
 _capacity_hint: dict[tuple, int] = {}
-_pinned: Optional[Tensor] = None
-_pinned_next = 0
-_PINNED_SLOTS = 256
 _segment_hint: dict[tuple, int] = {}
+_pending: dict[tuple, "weakref.ref"] = {}       # last deferred (unverified) state per shape key
+
+# Pinned host slots for the asynchronous instance count: every RasterOutputState OWNS its slot for as
+# long as it lives (a captured CUDA graph keeps writing to it on every replay) and hands it back to the
+# pool when it is garbage collected -- no ring, no aliasing.
+_PINNED_BLOCK = 64
+_pinned_blocks: list[Tensor] = []
+_pinned_free: list[Tensor] = []
+_pool_lock = threading.Lock()
+
+# SH convention the rasterizer evaluates coefficients in (include/pixelsplat_b200.h PS_SH_BASIS_*).
+_SH_BASIS = convention_id(os.environ.get("PIXELSPLAT_B200_SH_BASIS", "3dgs"))
 
 
 def set_capacity_check(mode: str) -> None:
@@ -41,13 +56,31 @@ def set_capacity_check(mode: str) -> None:
     _CHECK_MODE = mode
 
 
+def set_sh_basis(convention) -> None:
+    """Process-wide default SH convention of the rasterizer: "3dgs" (upstream 3DGS basis, the default) or
+    "e3nn" (the basis the reference's rotate_sh rotates in; see pixelsplat_b200/sh.py).  The drop-in
+    `GaussianRasterizationSettings` has no field for it (it mirrors the extension's NamedTuple), hence a
+    module switch; `rasterize_gaussians(sh_basis=...)` overrides it per call."""
+    global _SH_BASIS
+    _SH_BASIS = convention_id(convention)
+
+
+def get_sh_basis() -> int:
+    return _SH_BASIS
+
+
 def _pinned_slot() -> Tensor:
-    global _pinned, _pinned_next
-    if _pinned is None:
-        _pinned = torch.zeros(2 * _PINNED_SLOTS, dtype=torch.int64).pin_memory()
-    slot = _pinned[2 * _pinned_next:2 * _pinned_next + 2]
-    _pinned_next = (_pinned_next + 1) % _PINNED_SLOTS
-    return slot
+    with _pool_lock:
+        if not _pinned_free:
+            block = torch.zeros(2 * _PINNED_BLOCK, dtype=torch.int64).pin_memory()
+            _pinned_blocks.append(block)
+            _pinned_free.extend(block[2 * i:2 * i + 2] for i in range(_PINNED_BLOCK))
+        return _pinned_free.pop()
+
+
+def _release_slot(slot: Tensor) -> None:
+    with _pool_lock:
+        _pinned_free.append(slot)
 
 
 def _ptr(t: Optional[Tensor]):
@@ -71,6 +104,8 @@ class RasterOutputState:
         self.desc, self.geom, self.binning, self.image = desc, geom, binning, image
         self.n_host, self.event, self.hint_key = n_host, event, hint_key
         self.verified = False
+        # the slot returns to the pool when this state dies; until then nothing else writes to it
+        weakref.finalize(self, _release_slot, n_host)
 
     def raw_state(self) -> _lib.RasterState:
         return _lib.RasterState(self.geom.data_ptr(), self.geom.numel(), self.binning.data_ptr(),
@@ -138,21 +173,37 @@ class RasterOutputState:
         )
 
 
-def _make_desc(S, V, P, M, deg, sh_layout, cov_layout, H, W, capacity, sort_impl, seg_hint=0) -> _lib.RasterDesc:
-    return _lib.RasterDesc(S, V, P, M, deg, sh_layout, cov_layout, H, W, sort_impl, seg_hint, capacity)
+def _make_desc(S, V, P, M, deg, sh_layout, cov_layout, H, W, capacity, sort_impl, seg_hint=0,
+               sh_basis=0) -> _lib.RasterDesc:
+    return _lib.RasterDesc(S, V, P, M, deg, sh_layout, cov_layout, H, W, sort_impl, seg_hint, capacity,
+                           sh_basis, 0)
 
 
 def _forward_native(means, cov, opac, sh, cams, S, V, P, M, deg, sh_layout, cov_layout, H, W,
-                    sort_impl, want_radii):
+                    sort_impl, want_radii, sh_basis=0, backward_follows=False):
+    dev = means.device
+    with torch.cuda.device(dev):            # the library works on the CURRENT device
+        return _forward_on_device(means, cov, opac, sh, cams, S, V, P, M, deg, sh_layout, cov_layout, H, W,
+                                  sort_impl, want_radii, sh_basis, backward_follows)
+
+
+def _forward_on_device(means, cov, opac, sh, cams, S, V, P, M, deg, sh_layout, cov_layout, H, W,
+                       sort_impl, want_radii, sh_basis, backward_follows):
     dev = means.device
     key = (dev.index, S, V, P, H, W)
+    capturing = torch.cuda.is_current_stream_capturing()
+    prev = _pending.pop(key, None)
+    if prev is not None and not capturing:
+        prev = prev()
+        if prev is not None:
+            prev.verify()                   # deferred check of the previous forward of this shape
     capacity = _capacity_hint.get(key)
     if capacity is None:
         capacity = max(4096, 3 * S * V * P)
     stream = torch.cuda.current_stream(dev)
     while True:
         desc = _make_desc(S, V, P, M, deg, sh_layout, cov_layout, H, W, capacity, sort_impl,
-                          min(_segment_hint.get(key, 0), 1 << 30))
+                          min(_segment_hint.get(key, 0), 1 << 30), sh_basis)
         sz = _lib.sizes(desc)
         geom = torch.empty(sz.geom_bytes, dtype=torch.uint8, device=dev)
         binning = torch.empty(sz.binning_bytes, dtype=torch.uint8, device=dev)
@@ -181,7 +232,8 @@ def _forward_native(means, cov, opac, sh, cams, S, V, P, M, deg, sh_layout, cov_
         event = torch.cuda.Event()
         event.record(stream)
         st = RasterOutputState(desc, geom, binning, image, n_host, event, key)
-        if _CHECK_MODE == "deferred" and key in _capacity_hint:
+        if _CHECK_MODE == "deferred" and key in _capacity_hint and backward_follows:
+            _pending[key] = weakref.ref(st)
             return color, radii, st
         n = st.num_instances()
         if n <= capacity:
@@ -196,9 +248,10 @@ def _forward_native(means, cov, opac, sh, cams, S, V, P, M, deg, sh_layout, cov_
 class _RasterizeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means, cov, opac, sh, means2d, cams, S, V, P, M, deg, sh_layout, cov_layout,
-                H, W, sort_impl, state_out):
+                H, W, sort_impl, state_out, sh_basis):
+        backward_follows = any(ctx.needs_input_grad[:5])
         color, radii, st = _forward_native(means, cov, opac, sh, cams, S, V, P, M, deg, sh_layout,
-                                           cov_layout, H, W, sort_impl, True)
+                                           cov_layout, H, W, sort_impl, True, sh_basis, backward_follows)
         ctx.save_for_backward(means, cov, opac, sh)
         ctx.cams, ctx.st = cams, st
         ctx.want_m2d = means2d is not None and means2d.requires_grad
@@ -234,13 +287,14 @@ class _RasterizeFn(torch.autograd.Function):
         grads = _lib.RasterGrads(d_means.data_ptr(), d_cov.data_ptr(), d_opac.data_ptr(),
                                  d_sh.data_ptr(), d_m2d.data_ptr() if d_m2d is not None else None)
         state = st.raw_state()
-        stream = torch.cuda.current_stream(dev)
-        rc = _lib.lib.ps_raster_backward(ctypes.byref(desc), ctypes.byref(inputs), ctypes.byref(state),
-                                         ctypes.c_void_p(d_color.data_ptr()),
-                                         ctypes.c_void_p(scratch.data_ptr()), scratch.numel(),
-                                         ctypes.byref(grads), ctypes.c_void_p(stream.cuda_stream))
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            rc = _lib.lib.ps_raster_backward(ctypes.byref(desc), ctypes.byref(inputs), ctypes.byref(state),
+                                             ctypes.c_void_p(d_color.data_ptr()),
+                                             ctypes.c_void_p(scratch.data_ptr()), scratch.numel(),
+                                             ctypes.byref(grads), ctypes.c_void_p(stream.cuda_stream))
         _lib.check(rc, "ps_raster_backward")
-        return (d_means, d_cov, d_opac, d_sh, d_m2d) + (None,) * 12
+        return (d_means, d_cov, d_opac, d_sh, d_m2d) + (None,) * 13
 
 
 def rasterize_gaussians(
@@ -263,6 +317,7 @@ def rasterize_gaussians(
     sort_impl: int = 0,
     state_out: Optional[list] = None,
     means2d: Optional[Tensor] = None,       # [S*V, P, 3] gradient holder (upstream's means2D)
+    sh_basis=None,                          # "3dgs" / "e3nn"; None = the module default (set_sh_basis)
 ) -> tuple[Tensor, Tensor]:
     """Batched differentiable rasterization: S scenes x V views in one set of launches.
     Returns (color [S*V, 3, H, W], radii [S*V, P] int32)."""
@@ -301,7 +356,7 @@ def rasterize_gaussians(
         raise ValueError(f"means2d must be [S*V, P, 3], got {tuple(means2d.shape)}")
     return _RasterizeFn.apply(means, covariances, opacities, colors, means2d, cams, S, V, P, M,
                               int(sh_degree), sh_layout, cov_layout, int(H), int(W), int(sort_impl),
-                              state_out)
+                              state_out, _SH_BASIS if sh_basis is None else convention_id(sh_basis))
 
 
 # ------------------------------------------------------------------ drop-in extension surface

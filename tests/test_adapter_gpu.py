@@ -1,6 +1,6 @@
 """GPU parity tests of the fused GaussianAdapter (csrc/gaussian_adapter.cu).
 
-Against the REFERENCE module's golden outputs (tests/golden/adapter_v1.npz; float64 and float32 runs
+Against the REFERENCE module's golden outputs (tests/golden/adapter_v2.npz; float64 and float32 runs
 of /root/reference's GaussianAdapter with the e3nn-based `rotate_sh` factored out -- e3nn is absent
 offline, so the SH rotation is compared against this package's own torch path only, and against its
 defining properties in tests/test_adapter_cpu.py).
@@ -20,7 +20,7 @@ from tests.util import rel_err
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-GOLD = np.load(Path(__file__).resolve().parent / "golden" / "adapter_v1.npz")
+GOLD = np.load(Path(__file__).resolve().parent / "golden" / "adapter_v2.npz")
 IMAGE_SHAPE = (48, 64)
 OUT_KEYS = ("means", "covariances", "scales", "opacities", "harmonics")
 LEAVES = ("coordinates", "depths", "opacities", "raw")
@@ -43,15 +43,13 @@ def _run(ad, c, fused=True, rotate=True):
 
 
 @pytest.mark.parametrize("case", ["generic", "diverging"])
-def test_fused_adapter_matches_reference(case, monkeypatch):
+def test_fused_adapter_matches_reference(case):
+    """Every output and gradient, SH rotation included (the golden's rotate_sh is the reference's function
+    body on the restated e3nn functions, oracle/make_adapter_golden.py)."""
     from pixelsplat_b200 import _lib
-    from pixelsplat_b200.encoder import gaussian_adapter as ga
-    # factor the SH rotation out exactly as the golden generator did
-    monkeypatch.setattr(ga, "camera_sh_rotations",
-                        lambda E, degree: torch.eye((degree + 1) ** 2, device=E.device).repeat(E.shape[0], 1, 1))
     before = _lib.lib.ps_launch_count()
     g, grads = _run(_adapter(), gu.adapter_case(case=case))
-    assert _lib.lib.ps_launch_count() == before + 2          # one forward, one backward kernel
+    assert _lib.lib.ps_launch_count() == before + 3          # k_sh_rotation + one forward + one backward kernel
     for k in OUT_KEYS + ("rotations",):
         ours = getattr(g, k).detach().cpu().numpy()
         if k == "rotations":
@@ -84,10 +82,14 @@ def test_fused_equals_explicit_path_with_rotation(degree, r, spp):
 def test_device_rotation_matrices_equal_the_float64_fit():
     from pixelsplat_b200 import sh
     ext = gu.camera_rig(3, 3, "diverging")[0].reshape(9, 4, 4)
-    for degree in range(5):
-        D = sh.camera_sh_rotations(ext.to(DEV, torch.float32), degree)
-        ref = sh.sh_rotation_matrices(ext[:, :3, :3], degree)
-        assert D.shape == ref.shape and (D.cpu().double() - ref).abs().max() < 2e-6
+    for convention in ("e3nn", "3dgs"):
+        for degree in range(5):
+            D = sh.camera_sh_rotations(ext.to(DEV, torch.float32), degree, convention)
+            ref = sh.sh_rotation_matrices(ext[:, :3, :3], degree, convention)
+            assert D.shape == ref.shape and (D.cpu().double() - ref).abs().max() < 2e-6
+    # the reference's convention: the degree-1 block is the camera-to-world rotation itself
+    D = sh.camera_sh_rotations(ext.to(DEV, torch.float32), 1)
+    assert (D[:, 1:, 1:].cpu().double() - ext[:, :3, :3]).abs().max() < 2e-6
 
 
 def test_two_surfaces_and_unusual_broadcast_fall_back():

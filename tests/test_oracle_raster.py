@@ -212,3 +212,60 @@ def test_test_splatter_scene_renders():
         assert f.pre.radii[0] > 0 and abs(f.pre.xy[0, 0] - 63.5) < 1e-2 and abs(f.pre.xy[0, 1] - 63.5) < 1e-2
         imgs.append(f.color)
     assert not np.allclose(imgs[0], imgs[1])                # view-dependent colour
+
+
+@pytest.mark.parametrize("basis,rotation,consistent", [("3dgs", "3dgs", True), ("e3nn", "e3nn", True),
+                                                       ("3dgs", "e3nn", False)])
+def test_sh_convention_pairs_under_a_world_rotation(basis, rotation, consistent):
+    """Rotate the whole world (Gaussians, covariances, camera) by R and the SH coefficients by D(R): the image
+    must not change iff the rotation's convention matches the basis the rasterizer evaluates.  (3dgs, 3dgs)
+    and (e3nn, e3nn) are the two consistent pairs behind the PS_SH_BASIS_* switch; (3dgs basis, e3nn
+    rotation) is what the reference does if its rasterizer fork kept upstream's basis -- view-dependent
+    colour then changes with the frame, which is why ply_export.py:75 exports the DC band only.
+    Also checks the C oracle (f64) in the e3nn basis against torch autograd."""
+    from pixelsplat_b200 import sh as shm
+    conv = {"3dgs": 0, "e3nn": 1}
+    sc = synthetic.scene_random_frustum(seed=21, num_gaussians=300)
+    H, W = sc.image_shape
+    bg = torch.zeros(3, dtype=torch.float64)
+    q = torch.tensor([0.3, -0.5, 0.2, 0.79], dtype=torch.float64)
+    q = q / q.norm()
+    x, y, z, w = q
+    R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w), 2 * (x * y + z * w),
+                     1 - 2 * (x * x + z * z), 2 * (y * z - x * w), 2 * (x * z - y * w), 2 * (y * z + x * w),
+                     1 - 2 * (x * x + y * y)]).reshape(3, 3)
+
+    def render(means, cov, harm, ext):
+        a = rt.prepare_view(means, cov, harm, sc.opacities, ext, sc.intrinsics[0], sc.near[0], sc.far[0],
+                            dtype=torch.float64)
+        return rt.rasterize(a["means"], a["cov6"], a["opac"], a["sh"], None, a["vm"], a["pm"], a["campos"],
+                            a["tanfovx"], a["tanfovy"], bg, W, H, a["sh_degree"])[0], a
+
+    with ro.sh_basis(conv[basis]):
+        harm = sc.harmonics.double() * 4.0                       # make the view dependence visible
+        img0, a0 = render(sc.means.double(), sc.covariances.double(), harm, sc.extrinsics[0].double())
+        R4 = torch.eye(4, dtype=torch.float64)
+        R4[:3, :3] = R
+        harm_r = shm.rotate_sh(harm, R[None, None], rotation)
+        img1, _ = render(sc.means.double() @ R.T, R @ sc.covariances.double() @ R.T, harm_r,
+                         R4 @ sc.extrinsics[0].double())
+        diff = float((img0 - img1).abs().max())
+        # C oracle in this basis == torch (forward + SH / mean gradients)
+        n = lambda t: t.detach().numpy()
+        leaves = {k: a0[k].clone().requires_grad_(True) for k in ("means", "cov6", "opac", "sh")}
+        color, _ = rt.rasterize(leaves["means"], leaves["cov6"], leaves["opac"], leaves["sh"], None, a0["vm"],
+                                a0["pm"], a0["campos"], a0["tanfovx"], a0["tanfovy"], bg, W, H, a0["sh_degree"])
+        gimg = torch.randn(3, H, W, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
+        (color * gimg).sum().backward()
+        f = ro.forward(n(a0["means"]), n(a0["cov6"]), n(a0["opac"]), n(a0["sh"]), None, n(a0["vm"]), n(a0["pm"]),
+                       n(a0["campos"]), a0["tanfovx"], a0["tanfovy"], n(bg), W, H, a0["sh_degree"], dtype=np.float64)
+        b = ro.backward(f, n(gimg), n(a0["means"]), n(a0["cov6"]), n(a0["sh"]), n(a0["vm"]), n(a0["pm"]),
+                        n(a0["campos"]), a0["tanfovx"], a0["tanfovy"], n(bg), W, H, a0["sh_degree"])
+        assert np.abs(f.color - n(color)).max() < 1e-12
+        assert util.rel_err(b.dL_dsh, n(leaves["sh"].grad)) < 1e-10
+        assert util.rel_err(b.dL_dmeans, n(leaves["means"].grad)) < 1e-6
+    assert rt.SH_CONVENTION == 0
+    if consistent:
+        assert diff < 1e-6, diff            # float64 render; residual = conditioning of the 2D conic inverse
+    else:
+        assert diff > 1e-3, diff

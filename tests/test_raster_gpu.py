@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _native(a, bg, H, W, sort_impl=0, d_img=None, want_state=True):
+def _native(a, bg, H, W, sort_impl=0, d_img=None, want_state=True, sh_basis=None):
     from pixelsplat_b200.rasterizer import rasterize_gaussians
     t = lambda x: x.to(DEV)
     leaves = dict(means=t(a["means"])[None].clone().requires_grad_(True),
@@ -37,7 +37,7 @@ def _native(a, bg, H, W, sort_impl=0, d_img=None, want_state=True):
         tanfov=torch.tensor([[a["tanfovx"], a["tanfovy"]]], device=DEV),
         background=torch.tensor([bg], dtype=torch.float32, device=DEV), image_shape=(H, W),
         views_per_scene=1, sh_degree=a["sh_degree"], use_sh=use_sh, sort_impl=sort_impl,
-        state_out=states, means2d=m2d)
+        state_out=states, means2d=m2d, sh_basis=sh_basis)
     grads = None
     if d_img is not None:
         (color * torch.as_tensor(d_img, device=DEV)[None]).sum().backward()
@@ -46,9 +46,9 @@ def _native(a, bg, H, W, sort_impl=0, d_img=None, want_state=True):
     return color[0].detach().cpu().numpy(), radii[0].cpu().numpy(), states[0], grads
 
 
-def _check_forward(a, bg, H, W, sort_impl=0):
+def _check_forward(a, bg, H, W, sort_impl=0, sh_basis=None):
     f = util.oracle_forward(a, bg, W, H)
-    color, radii, st, _ = _native(a, bg, H, W, sort_impl)
+    color, radii, st, _ = _native(a, bg, H, W, sort_impl, sh_basis=sh_basis)
     im = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in st.intermediates().items()}
     vis = f.pre.radii > 0
     # ---- bit-exact integer / index work
@@ -80,11 +80,11 @@ def _check_forward(a, bg, H, W, sort_impl=0):
     return f, color
 
 
-def _check_backward(a, bg, H, W, seed=1, tol=2e-3):
+def _check_backward(a, bg, H, W, seed=1, tol=2e-3, sh_basis=None):
     f = util.oracle_forward(a, bg, W, H)
     d_img = np.random.default_rng(seed).standard_normal((3, H, W)).astype(np.float32)
     b = util.oracle_backward(f, a, d_img, bg, W, H)
-    _, _, _, g = _native(a, bg, H, W, 0, d_img)
+    _, _, _, g = _native(a, bg, H, W, 0, d_img, sh_basis=sh_basis)
     use_sh = a["sh"] is not None
     errs = dict(means=util.rel_err(g["means"], b.dL_dmeans), cov=util.rel_err(g["cov"], b.dL_dcov6),
                 opac=util.rel_err(g["opac"], b.dL_dopacity),
@@ -114,6 +114,24 @@ def test_lower_sh_degrees(deg):
     a = util.view_args(sc)
     _check_forward(a, (0.0, 0.0, 0.0), *sc.image_shape)
     _check_backward(a, (0.0, 0.0, 0.0), *sc.image_shape)
+
+
+@pytest.mark.parametrize("deg", [1, 2, 4])
+def test_e3nn_sh_basis_matches_oracle(deg):
+    """PS_SH_BASIS_E3NN (y polar, no Condon-Shortley sign: the basis the reference's rotate_sh rotates in,
+    sh_rotation.py:18-22): rgb stays bit-exact against the oracle evaluated in the same convention, gradients
+    within the usual bar; and it is a different image from the default basis."""
+    from oracle import raster_oracle as ro
+    sc = synthetic.scene_random_frustum(seed=40 + deg, sh_degree=deg)
+    sc.harmonics *= 3.0
+    a = util.view_args(sc)
+    with ro.sh_basis(1):
+        _, color_e = _check_forward(a, (0.0, 0.0, 0.0), *sc.image_shape, sh_basis="e3nn")
+        _check_backward(a, (0.0, 0.0, 0.0), *sc.image_shape, sh_basis="e3nn")
+    color_g, _, _, _ = _native(a, (0.0, 0.0, 0.0), *sc.image_shape)
+    assert np.abs(color_e - color_g).max() > 1e-2
+    with pytest.raises(ValueError, match="unknown SH convention"):
+        _native(a, (0.0, 0.0, 0.0), *sc.image_shape, sh_basis="opengl")
 
 
 def test_colors_precomp_path():
