@@ -134,6 +134,8 @@ typedef struct ps_raster_layout {
                              alpha >= 1/255 box -- the compositor's cull record                */
     size_t color;         /* image: f32 [S*V*3*H*W] copy of the rendered colour (the backward's
                              forward-order prefix form needs C . dL/dC per pixel)              */
+    size_t run_state;     /* image: f32x4 [S*V*3*H*W] (T, Cr, Cg, Cb) in front of list runs 1..3 when the
+                             compositor cuts a tile's list into runs (small batches)            */
 } ps_raster_layout;
 
 typedef struct ps_raster_grads {
@@ -154,6 +156,13 @@ PS_API const char *ps_last_error(void); /* thread-local, valid until the next fa
 PS_API unsigned long long ps_launch_count(void);
 PS_API void ps_timing_enable(int on);
 PS_API int ps_timing_read(float *ms);
+
+/* Process-wide tunables of the compositor, for A/B measurements and tests (defaults are automatic):
+ *   "composite_impl"      2 = warp-task compositor (default), 1 = round-1 CTA-per-tile compositor;
+ *   "composite_segments"  0 = automatic (default), 1 | 2 | 4 = list runs per warp task.
+ * Takes effect for forwards issued afterwards (a backward uses the split its forward used only if the option is
+ * unchanged in between).  Also read once from PIXELSPLAT_B200_COMPOSITE / PIXELSPLAT_B200_SEGMENTS. */
+PS_API int ps_set_option(const char *name, int value);
 
 /* Workspace sizes / layout for a descriptor. */
 PS_API int ps_raster_sizes_query(const ps_raster_desc *desc, ps_raster_sizes *out);

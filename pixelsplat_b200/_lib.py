@@ -54,7 +54,7 @@ class RasterLayout(ctypes.Structure):
     _fields_ = [(n, ctypes.c_size_t) for n in (
         "depth", "radii", "xy", "conic_opacity", "rgb", "rect", "clamped", "tile_count",
         "tile_start", "tile_cursor", "n_instances", "vis_pairs", "vis_any", "keys", "keys_alt", "final_T",
-        "n_contrib", "cull", "color")]
+        "n_contrib", "cull", "color", "run_state")]
 
 
 class EpipolarDesc(ctypes.Structure):
@@ -89,7 +89,7 @@ EXPORTS = ("ps_version", "ps_last_error", "ps_raster_sizes_query", "ps_raster_la
            "ps_timing_enable", "ps_timing_read", "ps_epipolar_geometry",
            "ps_epipolar_attention_forward", "ps_epipolar_attention_backward",
            "ps_self_attention_forward", "ps_gaussian_adapter_forward", "ps_gaussian_adapter_backward",
-           "ps_sh_rotation_matrices")
+           "ps_sh_rotation_matrices", "ps_set_option")
 
 
 class NativeLibraryMissing(ImportError):
@@ -134,6 +134,8 @@ def _load() -> ctypes.CDLL:
     lib.ps_gaussian_adapter_backward.restype = ctypes.c_int
     lib.ps_sh_rotation_matrices.argtypes = [ctypes.c_int32] * 4 + [ctypes.c_void_p] * 5
     lib.ps_sh_rotation_matrices.restype = ctypes.c_int
+    lib.ps_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    lib.ps_set_option.restype = ctypes.c_int
     for f in ("ps_raster_sizes_query", "ps_raster_layout_query", "ps_raster_forward", "ps_raster_backward"):
         getattr(lib, f).restype = ctypes.c_int
     return lib
@@ -151,6 +153,19 @@ def check(rc: int, what: str) -> None:
         msg = lib.ps_last_error().decode("utf-8", "replace")
         exc = ValueError if rc == 1 else NativeError
         raise exc(f"{what}: {_ERR_NAMES.get(rc, rc)}: {msg}")
+
+
+def on_device(device, fn, *args) -> int:
+    """Calls a library entry point with `device` as the CURRENT CUDA device: the library creates its side
+    stream / events and sets kernel attributes on the current device, so a tensor living on another GPU than
+    the caller's current one must switch first (torch.cuda.device is a no-op when it already is current)."""
+    import torch
+    with torch.cuda.device(device):
+        return fn(*args)
+
+
+def set_option(name: str, value: int) -> None:
+    check(lib.ps_set_option(name.encode(), int(value)), "ps_set_option")
 
 
 def sizes(desc: RasterDesc) -> RasterSizes:

@@ -33,10 +33,13 @@ struct ImageState {
     float *final_T;           // [S*V*H*W]
     uint32_t *n_contrib;      // [S*V*H*W]
     float *color;             // [S*V*3*H*W] copy of the rendered colour (backward's forward-order prefix form)
+    float4 *run_state;        // [S*V*(kMaxSegments-1)*H*W] (T, Cr, Cg, Cb) in front of list runs 1.. (segK > 1)
 };
 
+constexpr int kMaxSegments = 4;   // list runs per warp task (raster_composite2.cu)
+
 struct Dims {
-    int S, V, P, M, deg, sh_layout, cov_layout, H, W, gx, gy, tiles, sh_basis;
+    int S, V, P, M, deg, sh_layout, cov_layout, H, W, gx, gy, tiles, sh_basis, segK;
     long long capacity;
 };
 
@@ -75,14 +78,9 @@ void count_launch();
 
 // Once-per-DEVICE flags (a host process may drive several GPUs; kernel attributes and the library's
 // side stream are per device).  `mask` is a caller-owned static, one bit per device ordinal.
-inline bool first_use_on_device(unsigned long long &mask) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const unsigned long long bit = 1ull << (dev & 63);
-    if (mask & bit) return false;
-    mask |= bit;
-    return true;
-}
+// Thread-safe: the test-and-set happens under a process-wide mutex (the caller then sets a kernel attribute,
+// which is idempotent, so a second thread racing past the flag at worst repeats it).
+bool first_use_on_device(unsigned long long &mask);
 
 #define PS_CUDA_CHECK(expr)                                                              \
     do {                                                                                 \
@@ -122,6 +120,8 @@ int launch_composite_backward_v1(const Dims &d, const Inputs &in, const Geom &g,
                                  const unsigned long long *keys, const ImageState &img,
                                  const float *d_color, const ViewGrads &vg, cudaStream_t st);
 int composite_impl();   // 1 = legacy, 2 = warp-task compositor (env PIXELSPLAT_B200_COMPOSITE, default 2)
+int set_composite_option(int which, int value);   // 0: impl (1 | 2), 1: segments (0 = auto | 1 | 2 | 4)
+int composite_segments(long long tasks);   // list runs per task (1, 2, 4) for a batch of `tasks` warp tasks
 int launch_preprocess_backward(const Dims &d, const Inputs &in, const Geom &g, const ViewGrads &vg,
                                const ps_raster_grads &out, cudaStream_t st);
 int launch_gradient_fill(const Dims &d, const ps_raster_grads &out, cudaStream_t st);

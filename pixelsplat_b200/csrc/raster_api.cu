@@ -1,7 +1,10 @@
 // extern "C" entry points of include/pixelsplat_b200.h: argument validation, workspace layout,
 // stage sequencing.  No torch types, no exceptions across the ABI.
 #include <cstdarg>
+#include <atomic>
 #include <cstdio>
+#include <cstring>
+#include <mutex>
 
 #include "ps_common.cuh"
 
@@ -19,9 +22,21 @@ void set_error(const char *fmt, ...) {
 static bool g_timing = false;
 static cudaEvent_t g_events[kNumMarks];
 static bool g_events_ready = false;
-static unsigned long long g_launches = 0;
+static std::atomic<unsigned long long> g_launches{0};
 
-void count_launch() { ++g_launches; }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static std::mutex g_once_mutex;
+
+bool first_use_on_device(unsigned long long &mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    std::lock_guard<std::mutex> lock(g_once_mutex);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
 
 void mark(int id, cudaStream_t st) {
     if (!g_timing) return;
@@ -36,9 +51,13 @@ void mark(int id, cudaStream_t st) {
 // the composite backward).  Fork/join with events, which also captures cleanly into CUDA graphs.
 // The library's side stream and its fork / join events, one set per device ordinal (created on first
 // use on that device; a host process may drive several GPUs).
+// The fork / join event pair is shared by every call on a device, so the enqueue of one forward (or backward)
+// -- record fork, side-stream work, record join, wait join -- must not interleave with another host thread's on
+// the same device: each entry point holds the device's mutex while it enqueues (host-side only; ~tens of us).
 struct SideCtx {
     cudaStream_t side = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
+    std::mutex enqueue;
 };
 static SideCtx g_side_ctx[64];
 
@@ -46,6 +65,7 @@ static int side_ready(SideCtx *&ctx) {
     int dev = 0;
     PS_CUDA_CHECK(cudaGetDevice(&dev));
     ctx = &g_side_ctx[dev & 63];
+    std::lock_guard<std::mutex> lock(g_once_mutex);
     if (ctx->side) return PS_OK;
     PS_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
     PS_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming));
@@ -106,6 +126,7 @@ static Dims make_dims(const ps_raster_desc *d) {
     r.tiles = r.gx * r.gy;
     r.capacity = d->instance_capacity;
     r.sh_basis = d->sh_basis;
+    r.segK = composite_segments((long long)r.S * r.V * r.tiles * 8);
     return r;
 }
 
@@ -140,6 +161,7 @@ static Layout make_layout(const ps_raster_desc *d) {
     L.off.final_T = take(px * 4);
     L.off.n_contrib = take(px * 4);
     L.off.color = take(px * 12);
+    L.off.run_state = take(px * 16 * (kMaxSegments - 1));
     L.sizes.image_bytes = o;
     // backward scratch: d_mean2d (8) + d_conic (16) + d_color (16) per (view, Gaussian)
     L.sizes.backward_bytes = align_up(vp * 8) + align_up(vp * 16) + align_up(vp * 16);
@@ -172,6 +194,7 @@ static ImageState make_image(const Layout &L, void *image) {
     im.final_T = reinterpret_cast<float *>(b + L.off.final_T);
     im.n_contrib = reinterpret_cast<uint32_t *>(b + L.off.n_contrib);
     im.color = reinterpret_cast<float *>(b + L.off.color);
+    im.run_state = reinterpret_cast<float4 *>(b + L.off.run_state);
     return im;
 }
 
@@ -217,7 +240,7 @@ PS_API int ps_version(void) { return 100; }
 
 PS_API const char *ps_last_error(void) { return g_error; }
 
-PS_API unsigned long long ps_launch_count(void) { return g_launches; }
+PS_API unsigned long long ps_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 PS_API void ps_timing_enable(int on) { g_timing = on != 0; }
 
@@ -232,6 +255,15 @@ PS_API int ps_timing_read(float *ms) {
     PS_CUDA_CHECK(cudaEventSynchronize(g_events[kMarkPreprocessBwd]));
     for (int i = 0; i < 7; ++i) PS_CUDA_CHECK(cudaEventElapsedTime(&ms[i], g_events[pairs[i][0]], g_events[pairs[i][1]]));
     return PS_OK;
+}
+
+PS_API int ps_set_option(const char *name, int value) {
+    if (!name) { set_error("ps_set_option: name is NULL"); return PS_ERR_INVALID_ARGUMENT; }
+    int rc = PS_ERR_INVALID_ARGUMENT;
+    if (!strcmp(name, "composite_impl")) rc = set_composite_option(0, value);
+    else if (!strcmp(name, "composite_segments")) rc = set_composite_option(1, value);
+    if (rc) set_error("ps_set_option: unknown option or bad value: %s = %d", name, value);
+    return rc;
 }
 
 PS_API int ps_raster_sizes_query(const ps_raster_desc *desc, ps_raster_sizes *out) {
@@ -266,9 +298,10 @@ PS_API int ps_raster_forward(const ps_raster_desc *desc, const ps_raster_inputs 
     unsigned long long *keys_alt = reinterpret_cast<unsigned long long *>(static_cast<char *>(state->binning) + L.off.keys_alt);
     const ImageState img = make_image(L, state->image);
 
-    mark(kMarkFwdStart, st);
     SideCtx *sc = nullptr;
     if ((rc = side_ready(sc))) return rc;
+    std::lock_guard<std::mutex> enqueue_lock(sc->enqueue);
+    mark(kMarkFwdStart, st);
     if ((rc = launch_preprocess(d, I, g, st))) return rc;
     mark(kMarkPreprocess, st);
     // fork: SH -> RGB of the on-screen Gaussians runs beside the binning (scan / scatter / sort);
@@ -319,9 +352,10 @@ PS_API int ps_raster_backward(const ps_raster_desc *desc, const ps_raster_inputs
     vg.d_mean2d = reinterpret_cast<float2 *>(sb);
     vg.d_conic = reinterpret_cast<float4 *>(sb + align_up(vp * 8));
     vg.d_color = reinterpret_cast<float4 *>(sb + align_up(vp * 8) + align_up(vp * 16));
-    mark(kMarkBwdStart, st);
     SideCtx *sc = nullptr;
     if ((rc = side_ready(sc))) return rc;
+    std::lock_guard<std::mutex> enqueue_lock(sc->enqueue);
+    mark(kMarkBwdStart, st);
     // fork: zero the output gradients on the side stream while the composite backward runs
     PS_CUDA_CHECK(cudaEventRecord(sc->fork, st));
     PS_CUDA_CHECK(cudaStreamWaitEvent(sc->side, sc->fork, 0));

@@ -227,6 +227,28 @@ __device__ __forceinline__ void gather_rows(const float *__restrict__ base, unsi
     }
 }
 
+// Asynchronous form of gather_rows: every element is one cp.async (LDGSTS, 4 bytes -- rows start on 4-byte
+// boundaries only), so the whole warp's 32 x sh_n floats are in flight at once instead of one L2 / HBM round
+// trip per batch of four rows, and the caller can do unrelated work before gather_rows_wait().
+__device__ __forceinline__ void gather_rows_async(const float *__restrict__ base, unsigned long long row_of_lane,
+                                                  int rows_valid, int sh_n, float *wrows, int row_stride, int lane) {
+    for (int r = 0; r < rows_valid; ++r) {
+        const unsigned long long rs = __shfl_sync(0xffffffffu, row_of_lane, r);
+        const float *src = base + rs * (unsigned long long)sh_n;
+        float *dst = wrows + r * row_stride;
+        for (int c = lane; c < sh_n; c += 32) {
+            const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(dst + c);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(src + c) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ void gather_rows_wait() {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+}
+
 // The inverse: write the warp's staged rows back to their scattered global rows.
 __device__ __forceinline__ void scatter_rows(float *__restrict__ base, unsigned long long row_of_lane,
                                              int rows_valid, int sh_n, const float *wrows, int row_stride, int lane) {

@@ -169,9 +169,8 @@ k_sh_color(Dims d, Inputs in, Geom geo, int row_stride) {
     const size_t sg = (size_t)scene * d.P + g;
     const int sh_n = 3 * d.M;
     float *wrows = s_rows + (size_t)warp * 32 * row_stride;
-    gather_rows(in.sh, (unsigned long long)sg, (int)min((long long)32, n - i0), sh_n, wrows, row_stride, lane);
-    __syncwarp();
-    if (!live) return;
+    // all 32 rows in flight at once (cp.async), the direction set-up below runs under their latency
+    gather_rows_async(in.sh, (unsigned long long)sg, (int)min((long long)32, n - i0), sh_n, wrows, row_stride, lane);
     const float sc = in.scale ? in.scale[vid] : 1.0f;
     const float m0 = in.means[3 * sg + 0], m1 = in.means[3 * sg + 1], m2 = in.means[3 * sg + 2];
     const float px = in.scale ? m0 * sc : m0, py = in.scale ? m1 * sc : m1, pz = in.scale ? m2 * sc : m2;
@@ -179,6 +178,8 @@ k_sh_color(Dims d, Inputs in, Geom geo, int row_stride) {
     const float ddx = px - cx, ddy = py - cy, ddz = pz - cz;
     const float len = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
     const float x = ddx / len, y = ddy / len, z = ddz / len;
+    gather_rows_wait();
+    if (!live) return;
     const float *row = wrows + lane * row_stride;
     float acc[3] = {0.0f, 0.0f, 0.0f};
     const int M = d.M, layout = d.sh_layout;

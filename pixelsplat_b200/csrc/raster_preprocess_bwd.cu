@@ -41,10 +41,8 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
     float *grow = in_place ? row : row + (size_t)kPreBwdThreads * row_stride;   // separate gradient rows when V > 1
 
     const int rows_valid = (int)min((long long)32, n - i0);
-    if (M > 0) {
-        gather_rows(in.sh, (unsigned long long)sg, rows_valid, sh_n, wrows, row_stride, lane);
-        __syncwarp();
-    }
+    // the SH rows stream into shared memory while the geometry part below runs; waited for at first use
+    if (M > 0) gather_rows_async(in.sh, (unsigned long long)sg, rows_valid, sh_n, wrows, row_stride, lane);
 
     float mx0 = 0.0f, my0 = 0.0f, mz0 = 0.0f;
     if (live) { mx0 = in.means[3 * sg + 0]; my0 = in.means[3 * sg + 1]; mz0 = in.means[3 * sg + 2]; }
@@ -53,7 +51,7 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
     float dmx = 0.0f, dmy = 0.0f, dmz = 0.0f, dop = 0.0f;
     float dcov[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     float dcol[3] = {0.0f, 0.0f, 0.0f};
-    bool sh_written = false;
+    bool sh_written = false, sh_ready = false;
 
     for (int v = 0; v < d.V; ++v) {
         const int vid = (int)scene * d.V + v;
@@ -64,11 +62,15 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
             const float2 t = vgr.d_mean2d[vg];
             m2[0] = t.x; m2[1] = t.y;
         }
-        if (!vis) continue;
-        const float *__restrict__ vm = in.view + 16 * vid;
-        const float *__restrict__ pm = in.proj + 16 * vid;
+        // (no `continue` for the views this Gaussian is not on screen in: the warp must stay convergent for the
+        //  shared-memory hand-over of the SH rows below)
+        float gx = 0.0f, gy = 0.0f, gz = 0.0f;
+        float4 gcol = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         const float sc = in.scale ? in.scale[vid] : 1.0f;
         const float px = mx0 * sc, py = my0 * sc, pz = mz0 * sc;
+        if (vis) {
+        const float *__restrict__ vm = in.view + 16 * vid;
+        const float *__restrict__ pm = in.proj + 16 * vid;
         const float tanfovx = in.tanfov[2 * vid], tanfovy = in.tanfov[2 * vid + 1];
         const float focal_x = (float)d.W / (2.0f * tanfovx), focal_y = (float)d.H / (2.0f * tanfovy);
         float s6[6];
@@ -78,7 +80,7 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
 
         const float2 g2 = vgr.d_mean2d[vg];
         const float4 gc = vgr.d_conic[vg];
-        const float4 gcol = vgr.d_color[vg];
+        gcol = vgr.d_color[vg];
         dop += gc.w;
 
         const float a = cv.a, b = cv.b, c = cv.c;
@@ -117,9 +119,9 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
         const float dL_dty = cv.clamp_y ? 0.0f : -focal_y * tz2 * dJ12;
         const float dL_dtz = -focal_x * tz2 * dJ00 - focal_y * tz2 * dJ11 +
                              (2.0f * focal_x * cv.ctx) * tz3 * dJ02 + (2.0f * focal_y * cv.cty) * tz3 * dJ12;
-        float gx = vm[0] * dL_dtx + vm[1] * dL_dty + vm[2] * dL_dtz;
-        float gy = vm[4] * dL_dtx + vm[5] * dL_dty + vm[6] * dL_dtz;
-        float gz = vm[8] * dL_dtx + vm[9] * dL_dty + vm[10] * dL_dtz;
+        gx = vm[0] * dL_dtx + vm[1] * dL_dty + vm[2] * dL_dtz;
+        gy = vm[4] * dL_dtx + vm[5] * dL_dty + vm[6] * dL_dtz;
+        gz = vm[8] * dL_dtx + vm[9] * dL_dty + vm[10] * dL_dtz;
 
         // screen-space mean through the perspective divide
         const float hx = pm[0] * px + pm[4] * py + pm[8] * pz + pm[12];
@@ -130,8 +132,13 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
         gx += (pm[0] * m_w - pm[3] * mul1) * g2.x + (pm[1] * m_w - pm[3] * mul2) * g2.y;
         gy += (pm[4] * m_w - pm[7] * mul1) * g2.x + (pm[5] * m_w - pm[7] * mul2) * g2.y;
         gz += (pm[8] * m_w - pm[11] * mul1) * g2.x + (pm[9] * m_w - pm[11] * mul2) * g2.y;
+        }   // vis (geometry part)
 
-        if (M > 0) {
+        if (M > 0 && !sh_ready) {          // warp-uniform; the rows have had the geometry math to arrive
+            gather_rows_wait();
+            sh_ready = true;
+        }
+        if (M > 0 && vis) {
             const float cx = in.campos[3 * vid], cy = in.campos[3 * vid + 1], cz = in.campos[3 * vid + 2];
             const float ddx = px - cx, ddy = py - cy, ddz = pz - cz;
             const float len2 = ddx * ddx + ddy * ddy + ddz * ddz;
@@ -167,7 +174,7 @@ k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out
             gx += ((len2 - ddx * ddx) * dLdx - ddy * ddx * dLdy - ddz * ddx * dLdz) * inv3;
             gy += (-ddx * ddy * dLdx + (len2 - ddy * ddy) * dLdy - ddz * ddy * dLdz) * inv3;
             gz += (-ddx * ddz * dLdx - ddy * ddz * dLdy + (len2 - ddz * ddz) * dLdz) * inv3;
-        } else {
+        } else if (vis) {
             dcol[0] += gcol.x; dcol[1] += gcol.y; dcol[2] += gcol.z;
         }
         dmx += gx * sc; dmy += gy * sc; dmz += gz * sc;

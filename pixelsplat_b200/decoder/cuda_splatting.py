@@ -57,7 +57,7 @@ def camera_setup(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tens
     scale = torch.empty((n,), dtype=torch.float32, device=dev)
     p = lambda t: ctypes.c_void_p(t.data_ptr())
     stream = torch.cuda.current_stream(dev)
-    rc = _lib.lib.ps_camera_setup(n, p(e), p(k), p(nr), p(fr), 1 if scale_invariant else 0, p(view),
+    rc = _lib.on_device(dev, _lib.lib.ps_camera_setup, n, p(e), p(k), p(nr), p(fr), 1 if scale_invariant else 0, p(view),
                                   p(proj), p(campos), p(tanfov), p(scale),
                                   ctypes.c_void_p(stream.cuda_stream))
     _lib.check(rc, "ps_camera_setup")
@@ -169,6 +169,22 @@ def _relative_disparity(depth: Tensor, near: Tensor, far: Tensor, eps: float = 1
     return 1 - (disp - disp_far) / (disp_near - disp_far + eps)
 
 
+def depth_colors(extrinsics: Tensor, gaussian_means: Tensor, near: Tensor, far: Tensor,
+                 mode: DepthRenderingMode = "depth") -> Tensor:
+    """The per-Gaussian "colour" render_depth_cuda composites (cuda_splatting.py:238-251): camera-space z
+    of every Gaussian, optionally as disparity / relative disparity / log.  [s, v] cameras over [s, g]
+    Gaussians -> [s, v, g].  Pure torch (any device)."""
+    w2c = extrinsics.inverse()                                      # [s, v, 4, 4]
+    fake = torch.einsum("svj,sgj->svg", w2c[:, :, 2, :3], gaussian_means) + w2c[:, :, 2, 3:4]
+    if mode == "disparity":
+        fake = 1 / fake
+    elif mode == "relative_disparity":
+        fake = _relative_disparity(fake, near[..., None], far[..., None])
+    elif mode == "log":
+        fake = fake.minimum(near[..., None]).maximum(far[..., None]).log()
+    return fake
+
+
 def render_depth_views(extrinsics, intrinsics, near, far, image_shape, gaussian_means,
                        gaussian_covariances, gaussian_opacities, scale_invariant=True,
                        mode: DepthRenderingMode = "depth") -> Tensor:
@@ -176,15 +192,7 @@ def render_depth_views(extrinsics, intrinsics, near, far, image_shape, gaussian_
     (cuda_splatting.py:238-269); because the colour depends on the camera, each view needs its
     own colour set, so the views are flattened into scenes here."""
     s, v = extrinsics.shape[:2]
-    w2c = extrinsics.inverse()                                      # [s, v, 4, 4]
-    z = torch.einsum("svj,sgj->svg", w2c[:, :, 2, :3], gaussian_means) + w2c[:, :, 2, 3:4]
-    fake = z
-    if mode == "disparity":
-        fake = 1 / fake
-    elif mode == "relative_disparity":
-        fake = _relative_disparity(fake, near[..., None], far[..., None])
-    elif mode == "log":
-        fake = fake.minimum(near[..., None]).maximum(far[..., None]).log()
+    fake = depth_colors(extrinsics, gaussian_means, near, far, mode)
     g = gaussian_means.shape[1]
     rep = lambda t: t[:, None].expand(s, v, *t.shape[1:]).reshape(s * v, *t.shape[1:])
     colors = fake.reshape(s * v, g, 1, 1).expand(s * v, g, 3, 1)

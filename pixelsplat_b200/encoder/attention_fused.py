@@ -50,7 +50,7 @@ def epipolar_geometry(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far:
     rd = torch.empty((b, v, ov, r, samples), dtype=torch.float32, device=dev)
     tr = torch.empty((b, v, ov, r, 2), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream(dev)
-    rc = _lib.lib.ps_epipolar_geometry(b, v, h, w, samples, _p(e), _p(k), _p(nr), _p(fr), _p(seg), _p(valid),
+    rc = _lib.on_device(dev, _lib.lib.ps_epipolar_geometry, b, v, h, w, samples, _p(e), _p(k), _p(nr), _p(fr), _p(seg), _p(valid),
                                        _p(rd), _p(tr), ctypes.c_void_p(stream.cuda_stream))
     _lib.check(rc, "ps_epipolar_geometry")
     return EpipolarGeometry(seg, valid, rd, tr, (h, w), samples)
@@ -122,7 +122,7 @@ class _EpipolarAttentionFn(torch.autograd.Function):
         mass = torch.empty((n, heads, v - 1), dtype=torch.float32, device=dev)
         lse = torch.empty((n, heads), dtype=torch.float32, device=dev)
         stream = torch.cuda.current_stream(dev)
-        rc = _lib.lib.ps_epipolar_attention_forward(ctypes.byref(desc), ctypes.byref(inputs), _p(z), _p(e),
+        rc = _lib.on_device(dev, _lib.lib.ps_epipolar_attention_forward, ctypes.byref(desc), ctypes.byref(inputs), _p(z), _p(e),
                                                     _p(mass), _p(lse), ctypes.c_void_p(stream.cuda_stream))
         _lib.check(rc, "ps_epipolar_attention_forward")
         ctx.save_for_backward(qt, pq, bias_c if bias_c is not None else torch.empty(0, device=dev), feat_cl,
@@ -150,7 +150,7 @@ class _EpipolarAttentionFn(torch.autograd.Function):
         dbias = torch.empty_like(bias) if ctx.has_bias else None
         dfeat = torch.zeros_like(feat_cl)
         stream = torch.cuda.current_stream(dev)
-        rc = _lib.lib.ps_epipolar_attention_backward(
+        rc = _lib.on_device(dev, _lib.lib.ps_epipolar_attention_backward,
             ctypes.byref(desc), ctypes.byref(inputs), _p(lse), _p(dz), _p(de), _p(dmass) if use_mass else None,
             _p(d_row), _p(dqt), _p(dpq), _p(dbias), _p(dfeat), ctypes.c_void_p(stream.cuda_stream))
         _lib.check(rc, "ps_epipolar_attention_backward")

@@ -91,7 +91,7 @@ class _GaussianAdapterFn(torch.autograd.Function):
         scales = torch.empty((nv, nr, ns, 3), dtype=torch.float32, device=dev)
         rot = torch.empty((nv, nr, 4), dtype=torch.float32, device=dev)
         stream = torch.cuda.current_stream(dev)
-        rc = _lib.lib.ps_gaussian_adapter_forward(ctypes.byref(desc), ctypes.byref(inputs), _p(means), _p(cov),
+        rc = _lib.on_device(dev, _lib.lib.ps_gaussian_adapter_forward, ctypes.byref(desc), ctypes.byref(inputs), _p(means), _p(cov),
                                                   _p(harm), _p(scales), _p(rot), ctypes.c_void_p(stream.cuda_stream))
         _lib.check(rc, "ps_gaussian_adapter_forward")
         ctx.save_for_backward(*tensors)
@@ -112,7 +112,7 @@ class _GaussianAdapterFn(torch.autograd.Function):
         d_depths = torch.empty_like(tensors[5])
         d_raw = torch.empty_like(tensors[6])
         stream = torch.cuda.current_stream(dev)
-        rc = _lib.lib.ps_gaussian_adapter_backward(ctypes.byref(desc), ctypes.byref(inputs), _p(d_means), _p(d_cov),
+        rc = _lib.on_device(dev, _lib.lib.ps_gaussian_adapter_backward, ctypes.byref(desc), ctypes.byref(inputs), _p(d_means), _p(d_cov),
                                                    _p(d_harm), _p(d_scales), _p(d_rot), _p(d_coord), _p(d_depths),
                                                    _p(d_raw), ctypes.c_void_p(stream.cuda_stream))
         _lib.check(rc, "ps_gaussian_adapter_backward")

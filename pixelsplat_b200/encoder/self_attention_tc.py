@@ -36,7 +36,7 @@ def _launch(qkv: Tensor, heads: int, scale: float, debug_mode: int = 0) -> Tenso
     else:
         out = torch.empty((n, L, inner), dtype=torch.float32, device=qkv.device)
     stream = torch.cuda.current_stream(qkv.device)
-    rc = _lib.lib.ps_self_attention_forward(n, L, heads, inner // heads, ctypes.c_void_p(qkv.data_ptr()),
+    rc = _lib.on_device(qkv.device, _lib.lib.ps_self_attention_forward, n, L, heads, inner // heads, ctypes.c_void_p(qkv.data_ptr()),
                                             ctypes.c_float(scale), ctypes.c_void_p(out.data_ptr()), debug_mode,
                                             ctypes.c_void_p(stream.cuda_stream))
     _lib.check(rc, "ps_self_attention_forward")

@@ -91,6 +91,105 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], bucket_bytes: int 
     return n
 
 
+class GradientReducer:
+    """DDP-style gradient averaging that OVERLAPS the backward pass (replaces Lightning's DDP strategy,
+    /root/reference/src/main.py:94-98, for the step harness).
+
+      * every parameter's `.grad` is a VIEW into one flat, pre-allocated buffer per bucket (no `torch.cat`
+        to build a message, no copy back afterwards);
+      * buckets are filled in REVERSE registration order (the order gradients become ready in backward); a
+        post-accumulate-grad hook counts a bucket's ready parameters and, when the last one lands, issues the
+        bucket's all-reduce asynchronously -- NCCL runs it on its own stream while backward keeps going;
+      * collectives are always issued in bucket order (identical on every rank); a bucket with a parameter that
+        is unused this step therefore holds back the later ones until `finish()`, which reduces whatever is
+        left (unused parameters contribute zeros, as with DDP's find_unused_parameters) and waits for all;
+    Averaging is a pre-scale by 1/world of the buffer (one in-place multiply per bucket) followed by a SUM
+    all-reduce, so it works on every backend (gloo has no AVG)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 8 << 20, process_group=None):
+        self.group = process_group
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+        self.world = dist.get_world_size(process_group) if self.active else 1
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets: list[dict] = []
+        self._handles = []
+        self._next = 0                                        # first bucket not yet launched this step
+        if not self.params:
+            return
+        cur, size = [], 0
+        for p in reversed(self.params):                      # last layers first: ready first in backward
+            nbytes = p.numel() * p.element_size()
+            if cur and (size + nbytes > bucket_bytes or p.dtype != cur[0].dtype or p.device != cur[0].device):
+                self._add_bucket(cur)
+                cur, size = [], 0
+            cur.append(p)
+            size += nbytes
+        if cur:
+            self._add_bucket(cur)
+        for bi, b in enumerate(self.buckets):
+            for p in b["params"]:
+                self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
+
+    def _add_bucket(self, plist):
+        flat = torch.zeros(sum(p.numel() for p in plist), dtype=plist[0].dtype, device=plist[0].device)
+        off = 0
+        for p in plist:
+            p.grad = flat[off:off + p.numel()].view_as(p)    # the gradient LIVES in the bucket
+            off += p.numel()
+        self.buckets.append(dict(params=plist, flat=flat, ready=0, work=None, launched=False))
+
+    def _make_hook(self, bi: int):
+        def hook(param):
+            b = self.buckets[bi]
+            b["ready"] += 1
+            # collectives must be issued in the SAME order on every rank: bucket order, never readiness order
+            # (a parameter that is unused on one rank would otherwise reorder that rank's all-reduces)
+            while self._next < len(self.buckets):
+                nb = self.buckets[self._next]
+                if nb["ready"] < len(nb["params"]):
+                    break
+                self._launch(nb)
+                self._next += 1
+        return hook
+
+    def _launch(self, b) -> None:
+        b["launched"] = True
+        if not self.active:
+            return
+        b["flat"].mul_(1.0 / self.world)
+        b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def zero_grad(self) -> None:
+        """Start of a step: zero the buffers IN PLACE (`.grad` stays a view; do not use set_to_none=True)."""
+        self._next = 0
+        for b in self.buckets:
+            b["flat"].zero_()
+            b["ready"], b["work"], b["launched"] = 0, None, False
+            off = 0
+            for p in b["params"]:
+                if p.grad is None or p.grad.data_ptr() != b["flat"].data_ptr() + off * b["flat"].element_size():
+                    p.grad = b["flat"][off:off + p.numel()].view_as(p)     # re-attach if someone replaced it
+                off += p.numel()
+
+    def finish(self) -> int:
+        """After backward: reduce the buckets that never completed (unused parameters) and wait for all.
+        Returns the number of collectives issued this step."""
+        n = 0
+        while self._next < len(self.buckets):                 # in bucket order, like the hooks
+            self._launch(self.buckets[self._next])
+            self._next += 1
+        for b in self.buckets:
+            if b["work"] is not None:
+                b["work"].wait()
+                n += 1
+        return n
+
+    def remove(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
 def aggregate_throughput(units_per_rank: Sequence[float] | float, seconds_max: float, world: int) -> float:
     """Whole-job throughput: all ranks' units over the slowest rank's time."""
     total = sum(units_per_rank) if not isinstance(units_per_rank, (int, float)) else units_per_rank * world

@@ -10,6 +10,18 @@ import zlib
 import torch
 
 
+def load_npz_refs(path) -> dict:
+    """np.load of a fixture whose writer stored byte-identical large arrays once (`key__ref` names the
+    first copy; oracle/make_render_args_golden.py)."""
+    import numpy as np
+    raw = np.load(path)
+    out = {k: raw[k] for k in raw.files if not k.endswith("__ref")}
+    for k in raw.files:
+        if k.endswith("__ref"):
+            out[k[:-5]] = out[str(raw[k])]
+    return out
+
+
 def seeded_like(name: str, shape, scale: float = 1.0, dtype=torch.float64) -> torch.Tensor:
     g = torch.Generator().manual_seed(zlib.crc32(name.encode()))
     return (torch.randn(tuple(shape), generator=g, dtype=torch.float64) * scale).to(dtype)

