@@ -206,6 +206,30 @@ PS_API int ps_raster_backward(const ps_raster_desc *desc, const ps_raster_inputs
                        void *scratch, size_t scratch_bytes, const ps_raster_grads *grads,
                        void *stream);
 
+/* ---- fused loss epilogue --------------------------------------------------
+ * The training loss the reference applies to the render, LossMse (/root/reference/src/loss/loss_mse.py:30-31,
+ * weight * mean((prediction - target)^2)), and the PSNR it logs (src/evaluation/metrics.py:11-19) need, per view,
+ * sum (C - t)^2 and sum (clip(C) - clip(t))^2.  ps_raster_forward_loss accumulates both in the compositor's
+ * epilogue (the image is not re-read for the loss; out_color may be NULL when nobody needs the pixels), and
+ * ps_raster_backward_loss forms dL/dC = grad_scale[view] * (C - target) inside the composite backward, so no
+ * gradient image exists as a tensor either.  Host side: pixelsplat_b200/loss.py. */
+#define PS_LOSS_SLOTS 64
+typedef struct ps_raster_loss {
+    const float *target; /* [S*V, 3, H, W] */
+    float *sums;         /* [S*V, 2, PS_LOSS_SLOTS]: partial sums, [.,0,.] raw, [.,1,.] clipped to [0, 1];
+                            zeroed by the call; sum over the last axis for the per-view totals          */
+} ps_raster_loss;
+
+PS_API int ps_raster_forward_loss(const ps_raster_desc *desc, const ps_raster_inputs *in,
+                                  const ps_raster_state *state, const ps_raster_loss *loss,
+                                  float *out_color /* or NULL */, int32_t *out_radii,
+                                  int64_t *n_instances_host, void *stream);
+PS_API int ps_raster_backward_loss(const ps_raster_desc *desc, const ps_raster_inputs *in,
+                                   const ps_raster_state *state, const float *target /* [S*V,3,H,W] */,
+                                   const float *grad_scale /* [S*V]: dL/d(sum of squares) * 2 */,
+                                   void *scratch, size_t scratch_bytes, const ps_raster_grads *grads,
+                                   void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Epipolar sampled cross-attention.
  * Replaces, inside EpipolarTransformer.forward

@@ -79,6 +79,13 @@ class AdapterInputs(ctypes.Structure):
         "extrinsics", "intrinsics", "sh_rotation", "sh_mask", "coordinates", "depths", "raw")]
 
 
+class RasterLoss(ctypes.Structure):
+    _fields_ = [("target", ctypes.c_void_p), ("sums", ctypes.c_void_p)]
+
+
+LOSS_SLOTS = 64
+
+
 class RasterGrads(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
         "d_means", "d_cov", "d_opacities", "d_sh", "d_means2d")]
@@ -89,7 +96,7 @@ EXPORTS = ("ps_version", "ps_last_error", "ps_raster_sizes_query", "ps_raster_la
            "ps_timing_enable", "ps_timing_read", "ps_epipolar_geometry",
            "ps_epipolar_attention_forward", "ps_epipolar_attention_backward",
            "ps_self_attention_forward", "ps_gaussian_adapter_forward", "ps_gaussian_adapter_backward",
-           "ps_sh_rotation_matrices", "ps_set_option")
+           "ps_sh_rotation_matrices", "ps_set_option", "ps_raster_forward_loss", "ps_raster_backward_loss")
 
 
 class NativeLibraryMissing(ImportError):
@@ -111,6 +118,13 @@ def _load() -> ctypes.CDLL:
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.ps_raster_backward.argtypes = [P(RasterDesc), P(RasterInputs), P(RasterState), ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_size_t, P(RasterGrads), ctypes.c_void_p]
+    lib.ps_raster_forward_loss.argtypes = [P(RasterDesc), P(RasterInputs), P(RasterState), P(RasterLoss),
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.ps_raster_backward_loss.argtypes = [P(RasterDesc), P(RasterInputs), P(RasterState), ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, P(RasterGrads),
+                                            ctypes.c_void_p]
+    lib.ps_raster_forward_loss.restype = ctypes.c_int
+    lib.ps_raster_backward_loss.restype = ctypes.c_int
     lib.ps_camera_setup.argtypes = [ctypes.c_int32] + [ctypes.c_void_p] * 4 + [ctypes.c_int32] + \
         [ctypes.c_void_p] * 6
     lib.ps_camera_setup.restype = ctypes.c_int

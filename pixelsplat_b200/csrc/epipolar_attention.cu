@@ -110,16 +110,60 @@ __device__ __forceinline__ void positional_encoding(float rd, int npe, float (&p
     }
 }
 
+// Sum over the 32 lanes of SUB per-lane values v[0..SUB-1] (SUB = 4 or 8); every lane receives the total of
+// v[lane & (SUB - 1)].  Halving butterflies on the low lane bits, plain butterflies on the rest.
+template <int SUB>
+__device__ __forceinline__ float transpose_reduce_sub(float (&v)[SUB], int lane) {
+#pragma unroll
+    for (int half = SUB / 2; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float keep = up ? v[i + half] : v[i];
+            const float send = up ? v[i] : v[i + half];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    float r = v[0];
+#pragma unroll
+    for (int o = SUB; o < 32; o <<= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    return r;
+}
+
+// max / sum over the SUB distinct values held by an aligned group of SUB lanes (replicated across groups)
+template <int SUB>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+    for (int o = SUB / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <int SUB>
+__device__ __forceinline__ float group_add(float v) {
+#pragma unroll
+    for (int o = SUB / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Round 2: the S samples of a segment are processed in SUB-CHUNKS of SUB samples (8 forward, 4 backward) instead
+// of all 32 at once.  Holding f[32][4] pinned both kernels at 255 registers = 8 warps per SM (12 % occupancy),
+// which is what bounded them: they are latency-bound on the bilinear gathers (ncu r01: 22-27 % issue-active).
+// With SUB samples in registers the forward needs <= 128 registers (16 warps / SM) and the backward <= 128 too;
+// the soft-max is already streaming (online max / sum), so sub-chunks only add rescales.  The positional-
+// encoding half of every score (and of d score) is evaluated once per other view with lane = sample, as before,
+// and parked in shared memory for the sub-chunks to pick up.
 struct __align__(16) EpiWarpSmem {
-    float p[32][4];          // soft-max numerators of the current chunk, [sample][head]
+    float p[8][4];           // soft-max numerators (forward) / probabilities (backward) of the sub-chunk
+    float dsub[8][4];        // backward: d score of the sub-chunk
+    float scpe[32][4];       // PE half of the scores (+ bias), [sample][head]; -inf beyond S
+    float dape[32][4];       // backward: PE half of d a (+ dmass)
+    float ds_all[32][4];     // backward: d score of all samples of this other view (for dpq)
     float pe[32][kMaxPE + 1];
     float pq[4][kMaxPE];
     float aux[4][kMaxPE];    // backward: d_e
-    float ds[32][4];         // backward: d score, [sample][head]
 };
 
-template <int HEADS>
-__global__ void __launch_bounds__(kEpiWarps * 32)
+template <int HEADS, int SUB>
+__global__ void __launch_bounds__(kEpiWarps * 32, 4)
 k_epi_attn_fwd(EpiParams P, int n_queries, float *__restrict__ z_out, float *__restrict__ e_out,
                float *__restrict__ mass_out, float *__restrict__ lse_out) {
     __shared__ EpiWarpSmem sm_all[kEpiWarps];
@@ -142,16 +186,15 @@ k_epi_attn_fwd(EpiParams P, int n_queries, float *__restrict__ z_out, float *__r
     __syncwarp();
 
     float m_run[HEADS], l_run[HEADS], z[HEADS][4], e_acc[3];   // e_acc: outputs lane, lane+32, lane+64
+    float mass_acc[HEADS];                                     // lane ov (< OV) accumulates the mass of view ov
 #pragma unroll
     for (int hd = 0; hd < HEADS; ++hd) {
-        m_run[hd] = -INFINITY; l_run[hd] = 0.0f;
+        m_run[hd] = -INFINITY; l_run[hd] = 0.0f; mass_acc[hd] = 0.0f;
         z[hd][0] = z[hd][1] = z[hd][2] = z[hd][3] = 0.0f;
     }
     e_acc[0] = e_acc[1] = e_acc[2] = 0.0f;
-    float mass_acc[HEADS];   // lane ov (< OV) accumulates mass of chunk ov
-
-#pragma unroll
-    for (int hd = 0; hd < HEADS; ++hd) mass_acc[hd] = 0.0f;
+    const int nsub = (P.S + SUB - 1) / SUB;
+    const int total_e = HEADS * P.npe;
 
     for (int ov = 0; ov < P.OV; ++ov) {
         const int o_view = ov < v ? ov : ov + 1;
@@ -160,93 +203,99 @@ k_epi_attn_fwd(EpiParams P, int n_queries, float *__restrict__ z_out, float *__r
         const bool ok = P.valid[ray] != 0;
         const float *fmap = P.feat + (size_t)(b * P.V + o_view) * R * kEpiC + 4 * lane;
 
-        // ---- gather the S samples (channels 4*lane..4*lane+3 of each)
-        float f[32][4];
+        // ---- PE half of the scores, lane = sample
+        {
+            float pe[kMaxPE];
+            const bool has_sample = lane < P.S;
+            positional_encoding(has_sample ? P.rd[ray * P.S + lane] : 0.0f, P.npe, pe);
 #pragma unroll
-        for (int s = 0; s < 32; ++s) {
-            f[s][0] = f[s][1] = f[s][2] = f[s][3] = 0.0f;
-            if (s < P.S && ok) {
-                const float u = ((float)s + 0.5f) / (float)P.S;
-                const Taps t = make_taps(sg.x + u * (sg.z - sg.x), sg.y + u * (sg.w - sg.y), P.h, P.w);
+            for (int j = 0; j < kMaxPE; ++j)
+                if (j < P.npe) sm.pe[lane][j] = has_sample ? pe[j] : 0.0f;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (t.off[k] >= 0) {
-                        const float4 a = ldg4(fmap + t.off[k]);
-                        f[s][0] += t.w[k] * a.x; f[s][1] += t.w[k] * a.y;
-                        f[s][2] += t.w[k] * a.z; f[s][3] += t.w[k] * a.w;
+            for (int hd = 0; hd < HEADS; ++hd) {
+                float sc = 0.0f;
+#pragma unroll
+                for (int j = 0; j < kMaxPE; ++j)
+                    if (j < P.npe) sc += sm.pq[hd][j] * pe[j];
+                if (P.bias) sc += P.bias[((size_t)n * HEADS + hd) * P.OV + ov];
+                sm.scpe[lane][hd] = has_sample ? sc : -INFINITY;
+            }
+        }
+        __syncwarp();
+
+        for (int sub = 0; sub < nsub; ++sub) {
+            // ---- gather SUB samples (channels 4*lane..4*lane+3 of each)
+            float f[SUB][4];
+#pragma unroll
+            for (int i = 0; i < SUB; ++i) {
+                const int s = sub * SUB + i;
+                f[i][0] = f[i][1] = f[i][2] = f[i][3] = 0.0f;
+                if (s < P.S && ok) {
+                    const float u = ((float)s + 0.5f) / (float)P.S;
+                    const Taps t = make_taps(sg.x + u * (sg.z - sg.x), sg.y + u * (sg.w - sg.y), P.h, P.w);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (t.off[k] >= 0) {
+                            const float4 a = ldg4(fmap + t.off[k]);
+                            f[i][0] += t.w[k] * a.x; f[i][1] += t.w[k] * a.y;
+                            f[i][2] += t.w[k] * a.z; f[i][3] += t.w[k] * a.w;
+                        }
                     }
                 }
             }
-        }
-        // ---- positional encoding of this lane's sample
-        float pe[kMaxPE];
-        const bool has_sample = lane < P.S;
-        positional_encoding(has_sample ? P.rd[ray * P.S + lane] : 0.0f, P.npe, pe);
-#pragma unroll
-        for (int j = 0; j < kMaxPE; ++j)
-            if (j < P.npe) sm.pe[lane][j] = has_sample ? pe[j] : 0.0f;
-
-        // ---- scores: lane s ends up with the score of sample s
-        float pnum[HEADS];
-        float scale_old[HEADS];
-#pragma unroll
-        for (int hd = 0; hd < HEADS; ++hd) {
-            float part[32];
-#pragma unroll
-            for (int s = 0; s < 32; ++s)
-                part[s] = qt[hd][0] * f[s][0] + qt[hd][1] * f[s][1] + qt[hd][2] * f[s][2] + qt[hd][3] * f[s][3];
-            float sc = transpose_reduce32(part, lane);
-#pragma unroll
-            for (int j = 0; j < kMaxPE; ++j)
-                if (j < P.npe) sc += sm.pq[hd][j] * pe[j];
-            if (P.bias) sc += P.bias[((size_t)n * HEADS + hd) * P.OV + ov];
-            if (!has_sample) sc = -INFINITY;
-            const float m_new = fmaxf(m_run[hd], warp_max(sc));
-            scale_old[hd] = __expf(m_run[hd] - m_new);          // exp(-inf) = 0 on the first chunk
-            pnum[hd] = has_sample ? __expf(sc - m_new) : 0.0f;
-            const float psum = warp_add(pnum[hd]);
-            l_run[hd] = l_run[hd] * scale_old[hd] + psum;
-            m_run[hd] = m_new;
-            sm.p[lane][hd] = pnum[hd];
-            if (lane == ov) mass_acc[hd] = psum;
-            else if (lane < ov) mass_acc[hd] *= scale_old[hd];
-        }
-        __syncwarp();
-        // ---- weighted sums
-#pragma unroll
-        for (int hd = 0; hd < HEADS; ++hd) {
-            z[hd][0] *= scale_old[hd]; z[hd][1] *= scale_old[hd];
-            z[hd][2] *= scale_old[hd]; z[hd][3] *= scale_old[hd];
-        }
-#pragma unroll
-        for (int s = 0; s < 32; ++s) {
-            float pw[4];
-            *reinterpret_cast<float4 *>(pw) = *reinterpret_cast<const float4 *>(sm.p[s]);
+            // ---- scores: every lane ends up with the score of sample sub*SUB + (lane & (SUB-1))
+            const int s_mine = sub * SUB + (lane & (SUB - 1));
+            float scale_old[HEADS];
 #pragma unroll
             for (int hd = 0; hd < HEADS; ++hd) {
-                z[hd][0] += pw[hd] * f[s][0]; z[hd][1] += pw[hd] * f[s][1];
-                z[hd][2] += pw[hd] * f[s][2]; z[hd][3] += pw[hd] * f[s][3];
-            }
-        }
-        // e[h][j] = sum_s p[s][h] * pe[s][j]; output index o = lane + 32*i -> (h, j) = (o / npe, o % npe)
-        {
-            const int total = HEADS * P.npe;
+                float part[SUB];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const int o = lane + 32 * i;
-                if (o < total) {
+                for (int i = 0; i < SUB; ++i)
+                    part[i] = qt[hd][0] * f[i][0] + qt[hd][1] * f[i][1] + qt[hd][2] * f[i][2] + qt[hd][3] * f[i][3];
+                const float sc = transpose_reduce_sub<SUB>(part, lane) + sm.scpe[s_mine][hd];   // -inf beyond S
+                const float m_new = fmaxf(m_run[hd], group_max<SUB>(sc));     // >= one finite score per sub-chunk
+                scale_old[hd] = __expf(m_run[hd] - m_new);                     // exp(-inf) = 0 on the first one
+                const float pnum = __expf(sc - m_new);                         // exp(-inf) = 0 beyond S
+                const float psum = group_add<SUB>(pnum);
+                l_run[hd] = l_run[hd] * scale_old[hd] + psum;
+                m_run[hd] = m_new;
+                if (lane < SUB) sm.p[lane][hd] = pnum;
+                if (lane <= ov) mass_acc[hd] = mass_acc[hd] * scale_old[hd] + (lane == ov ? psum : 0.0f);
+            }
+            __syncwarp();
+            // ---- weighted sums
+#pragma unroll
+            for (int hd = 0; hd < HEADS; ++hd) {
+                z[hd][0] *= scale_old[hd]; z[hd][1] *= scale_old[hd];
+                z[hd][2] *= scale_old[hd]; z[hd][3] *= scale_old[hd];
+            }
+#pragma unroll
+            for (int i = 0; i < SUB; ++i) {
+                float pw[4];
+                *reinterpret_cast<float4 *>(pw) = *reinterpret_cast<const float4 *>(sm.p[i]);
+#pragma unroll
+                for (int hd = 0; hd < HEADS; ++hd) {
+                    z[hd][0] += pw[hd] * f[i][0]; z[hd][1] += pw[hd] * f[i][1];
+                    z[hd][2] += pw[hd] * f[i][2]; z[hd][3] += pw[hd] * f[i][3];
+                }
+            }
+            // e[h][j] = sum_s p[s][h] * pe[s][j]; output index o = lane + 32*i -> (h, j) = (o / npe, o % npe)
+#pragma unroll
+            for (int i3 = 0; i3 < 3; ++i3) {
+                const int o = lane + 32 * i3;
+                if (o < total_e) {
                     const int hd = o / P.npe, j = o % P.npe;
                     float acc = 0.0f;
-                    for (int s = 0; s < 32; ++s) acc += sm.p[s][hd] * sm.pe[s][j];
-                    // scale_old of head hd: read through shared to keep indexing static-free
+#pragma unroll
+                    for (int i = 0; i < SUB; ++i) acc += sm.p[i][hd] * sm.pe[sub * SUB + i][j];
                     float so = 0.0f;
 #pragma unroll
                     for (int q = 0; q < HEADS; ++q) so = (q == hd) ? scale_old[q] : so;
-                    e_acc[i] = e_acc[i] * so + acc;
+                    e_acc[i3] = e_acc[i3] * so + acc;
                 }
             }
+            __syncwarp();
         }
-        __syncwarp();
     }
 
     // ---- normalise and store
@@ -258,18 +307,15 @@ k_epi_attn_fwd(EpiParams P, int n_queries, float *__restrict__ z_out, float *__r
         if (lane == 0) lse_out[(size_t)n * HEADS + hd] = m_run[hd] + __logf(l_run[hd]);
         if (mass_out && lane < P.OV) mass_out[((size_t)n * HEADS + hd) * P.OV + lane] = mass_acc[hd] * inv;
     }
-    {
-        const int total = HEADS * P.npe;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int o = lane + 32 * i;
-            if (o < total) {
-                const int hd = o / P.npe;
-                float lr = 1.0f;
+    for (int i3 = 0; i3 < 3; ++i3) {
+        const int o = lane + 32 * i3;
+        if (o < total_e) {
+            const int hd = o / P.npe;
+            float lr = 1.0f;
 #pragma unroll
-                for (int q = 0; q < HEADS; ++q) lr = (q == hd) ? l_run[q] : lr;
-                e_out[(size_t)n * total + o] = e_acc[i] / lr;
-            }
+            for (int q = 0; q < HEADS; ++q) lr = (q == hd) ? l_run[q] : lr;
+            e_out[(size_t)n * total_e + o] = e_acc[i3] / lr;
         }
     }
 }
@@ -279,9 +325,9 @@ k_epi_attn_fwd(EpiParams P, int n_queries, float *__restrict__ z_out, float *__r
 // outside by one elementwise pass).  Outputs: dqt, dpq, dbias, and d(feature map) accumulated with
 // 16-byte vector atomics (the map gradient is L2-resident; consecutive samples that fall in the
 // same bilinear cell are merged in registers first, which removes most of the atomics on short
-// epipolar segments).
-template <int HEADS>
-__global__ void __launch_bounds__(kEpiWarps * 32)
+// epipolar segments).  With lse known every sample is independent, so sub-chunks need no rescaling here.
+template <int HEADS, int SUB>
+__global__ void __launch_bounds__(kEpiWarps * 32, 4)
 k_epi_attn_bwd(EpiParams P, int n_queries, const float *__restrict__ lse, const float *__restrict__ dz,
                const float *__restrict__ de, const float *__restrict__ dmass, const float *__restrict__ Drow,
                float *__restrict__ dqt_out, float *__restrict__ dpq_out, float *__restrict__ dbias_out,
@@ -312,6 +358,7 @@ k_epi_attn_bwd(EpiParams P, int n_queries, const float *__restrict__ lse, const 
     }
     __syncwarp();
     float dpq_acc[3] = {0.0f, 0.0f, 0.0f};
+    const int nsub = (P.S + SUB - 1) / SUB;
 
     for (int ov = 0; ov < P.OV; ++ov) {
         const int o_view = ov < v ? ov : ov + 1;
@@ -321,56 +368,32 @@ k_epi_attn_bwd(EpiParams P, int n_queries, const float *__restrict__ lse, const 
         const size_t map_base = (size_t)(b * P.V + o_view) * R * kEpiC + 4 * lane;
         const float *fmap = P.feat + map_base;
 
-        float f[32][4];
-#pragma unroll
-        for (int s = 0; s < 32; ++s) {
-            f[s][0] = f[s][1] = f[s][2] = f[s][3] = 0.0f;
-            if (s < P.S && ok) {
-                const float u = ((float)s + 0.5f) / (float)P.S;
-                const Taps t = make_taps(sg.x + u * (sg.z - sg.x), sg.y + u * (sg.w - sg.y), P.h, P.w);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (t.off[k] >= 0) {
-                        const float4 a = ldg4(fmap + t.off[k]);
-                        f[s][0] += t.w[k] * a.x; f[s][1] += t.w[k] * a.y;
-                        f[s][2] += t.w[k] * a.z; f[s][3] += t.w[k] * a.w;
-                    }
-                }
-            }
-        }
-        float pe[kMaxPE];
-        const bool has_sample = lane < P.S;
-        positional_encoding(has_sample ? P.rd[ray * P.S + lane] : 0.0f, P.npe, pe);
-#pragma unroll
-        for (int j = 0; j < kMaxPE; ++j)
-            if (j < P.npe) sm.pe[lane][j] = has_sample ? pe[j] : 0.0f;
-
-#pragma unroll
-        for (int hd = 0; hd < HEADS; ++hd) {
-            float part[32];
-#pragma unroll
-            for (int s = 0; s < 32; ++s)
-                part[s] = qt[hd][0] * f[s][0] + qt[hd][1] * f[s][1] + qt[hd][2] * f[s][2] + qt[hd][3] * f[s][3];
-            float sc = transpose_reduce32(part, lane);
-#pragma unroll
-            for (int s = 0; s < 32; ++s)
-                part[s] = gz[hd][0] * f[s][0] + gz[hd][1] * f[s][1] + gz[hd][2] * f[s][2] + gz[hd][3] * f[s][3];
-            float da = transpose_reduce32(part, lane);
+        // ---- PE halves of the score and of d a, lane = sample
+        {
+            float pe[kMaxPE];
+            const bool has_sample = lane < P.S;
+            positional_encoding(has_sample ? P.rd[ray * P.S + lane] : 0.0f, P.npe, pe);
 #pragma unroll
             for (int j = 0; j < kMaxPE; ++j)
-                if (j < P.npe) { sc += sm.pq[hd][j] * pe[j]; da += sm.aux[hd][j] * pe[j]; }
-            if (P.bias) sc += P.bias[((size_t)n * HEADS + hd) * P.OV + ov];
-            if (dmass) da += dmass[((size_t)n * HEADS + hd) * P.OV + ov];
-            const float a = has_sample ? __expf(sc - lse_h[hd]) : 0.0f;
-            const float dsc = a * (da - D_h[hd]);
-            sm.p[lane][hd] = a;
-            sm.ds[lane][hd] = dsc;
-            const float dbias = warp_add(dsc);
-            if (dbias_out && lane == 0) dbias_out[((size_t)n * HEADS + hd) * P.OV + ov] = dbias;
+                if (j < P.npe) sm.pe[lane][j] = has_sample ? pe[j] : 0.0f;
+#pragma unroll
+            for (int hd = 0; hd < HEADS; ++hd) {
+                float sc = 0.0f, da = 0.0f;
+#pragma unroll
+                for (int j = 0; j < kMaxPE; ++j)
+                    if (j < P.npe) { sc += sm.pq[hd][j] * pe[j]; da += sm.aux[hd][j] * pe[j]; }
+                if (P.bias) sc += P.bias[((size_t)n * HEADS + hd) * P.OV + ov];
+                if (dmass) da += dmass[((size_t)n * HEADS + hd) * P.OV + ov];
+                sm.scpe[lane][hd] = has_sample ? sc : -INFINITY;
+                sm.dape[lane][hd] = da;
+                sm.ds_all[lane][hd] = 0.0f;
+            }
         }
         __syncwarp();
 
-        // dqt += sum_s ds[s] f[s];  d f[s] = sum_h a[s,h] dz_h + ds[s,h] qt_h  -> scatter to the taps
+        float dbias_acc[HEADS];
+#pragma unroll
+        for (int hd = 0; hd < HEADS; ++hd) dbias_acc[hd] = 0.0f;
         int cur_base = -0x7fffffff;
         float tap_acc[4][4];
         int tap_off[4] = {-1, -1, -1, -1};
@@ -385,43 +408,94 @@ k_epi_attn_bwd(EpiParams P, int n_queries, const float *__restrict__ lse, const 
                 tap_acc[k][0] = tap_acc[k][1] = tap_acc[k][2] = tap_acc[k][3] = 0.0f;
             }
         };
+
+        for (int sub = 0; sub < nsub; ++sub) {
+            float f[SUB][4];
 #pragma unroll
-        for (int s = 0; s < 32; ++s) {
-            float aw[4], dw[4];
-            *reinterpret_cast<float4 *>(aw) = *reinterpret_cast<const float4 *>(sm.p[s]);
-            *reinterpret_cast<float4 *>(dw) = *reinterpret_cast<const float4 *>(sm.ds[s]);
-            float df[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            for (int i = 0; i < SUB; ++i) {
+                const int s = sub * SUB + i;
+                f[i][0] = f[i][1] = f[i][2] = f[i][3] = 0.0f;
+                if (s < P.S && ok) {
+                    const float u = ((float)s + 0.5f) / (float)P.S;
+                    const Taps t = make_taps(sg.x + u * (sg.z - sg.x), sg.y + u * (sg.w - sg.y), P.h, P.w);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (t.off[k] >= 0) {
+                            const float4 a = ldg4(fmap + t.off[k]);
+                            f[i][0] += t.w[k] * a.x; f[i][1] += t.w[k] * a.y;
+                            f[i][2] += t.w[k] * a.z; f[i][3] += t.w[k] * a.w;
+                        }
+                    }
+                }
+            }
+            const int s_mine = sub * SUB + (lane & (SUB - 1));
 #pragma unroll
             for (int hd = 0; hd < HEADS; ++hd) {
+                float part[SUB];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    dq[hd][c] += dw[hd] * f[s][c];
-                    df[c] += aw[hd] * gz[hd][c] + dw[hd] * qt[hd][c];
+                for (int i = 0; i < SUB; ++i)
+                    part[i] = qt[hd][0] * f[i][0] + qt[hd][1] * f[i][1] + qt[hd][2] * f[i][2] + qt[hd][3] * f[i][3];
+                const float sc = transpose_reduce_sub<SUB>(part, lane) + sm.scpe[s_mine][hd];
+#pragma unroll
+                for (int i = 0; i < SUB; ++i)
+                    part[i] = gz[hd][0] * f[i][0] + gz[hd][1] * f[i][1] + gz[hd][2] * f[i][2] + gz[hd][3] * f[i][3];
+                const float da = transpose_reduce_sub<SUB>(part, lane) + sm.dape[s_mine][hd];
+                const float a = __expf(sc - lse_h[hd]);                 // 0 beyond S (score -inf)
+                const float dsc = a * (da - D_h[hd]);
+                if (lane < SUB) {
+                    sm.p[lane][hd] = a;
+                    sm.dsub[lane][hd] = dsc;
+                    sm.ds_all[s_mine][hd] = dsc;
+                }
+                dbias_acc[hd] += group_add<SUB>(dsc);
+            }
+            __syncwarp();
+
+            // dqt += sum_s ds[s] f[s];  d f[s] = sum_h a[s,h] dz_h + ds[s,h] qt_h  -> scatter to the taps
+#pragma unroll
+            for (int i = 0; i < SUB; ++i) {
+                const int s = sub * SUB + i;
+                float aw[4], dw[4];
+                *reinterpret_cast<float4 *>(aw) = *reinterpret_cast<const float4 *>(sm.p[i]);
+                *reinterpret_cast<float4 *>(dw) = *reinterpret_cast<const float4 *>(sm.dsub[i]);
+                float df[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int hd = 0; hd < HEADS; ++hd) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        dq[hd][c] += dw[hd] * f[i][c];
+                        df[c] += aw[hd] * gz[hd][c] + dw[hd] * qt[hd][c];
+                    }
+                }
+                if (s < P.S && ok) {
+                    const float u = ((float)s + 0.5f) / (float)P.S;
+                    const float sx = sg.x + u * (sg.z - sg.x), sy = sg.y + u * (sg.w - sg.y);
+                    const Taps t = make_taps(sx, sy, P.h, P.w);
+                    // identify the bilinear cell by its top-left tap position (may be outside)
+                    const float ix = sx * (float)P.w - 0.5f, iy = sy * (float)P.h - 0.5f;
+                    const int bx = (int)fminf(fmaxf(floorf(ix), -2.0f), (float)P.w + 1.0f);
+                    const int by = (int)fminf(fmaxf(floorf(iy), -2.0f), (float)P.h + 1.0f);
+                    const int base = by * (P.w + 4) + bx;
+                    if (base != cur_base) {
+                        flush();
+                        cur_base = base;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) tap_off[k] = t.off[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        tap_acc[k][0] += t.w[k] * df[0]; tap_acc[k][1] += t.w[k] * df[1];
+                        tap_acc[k][2] += t.w[k] * df[2]; tap_acc[k][3] += t.w[k] * df[3];
+                    }
                 }
             }
-            if (s < P.S && ok) {
-                const float u = ((float)s + 0.5f) / (float)P.S;
-                const Taps t = make_taps(sg.x + u * (sg.z - sg.x), sg.y + u * (sg.w - sg.y), P.h, P.w);
-                // identify the bilinear cell by its top-left tap position (may be outside)
-                const float ix = (sg.x + u * (sg.z - sg.x)) * (float)P.w - 0.5f;
-                const float iy = (sg.y + u * (sg.w - sg.y)) * (float)P.h - 0.5f;
-                const int bx = (int)fminf(fmaxf(floorf(ix), -2.0f), (float)P.w + 1.0f);
-                const int by = (int)fminf(fmaxf(floorf(iy), -2.0f), (float)P.h + 1.0f);
-                const int base = by * (P.w + 4) + bx;
-                if (base != cur_base) {
-                    flush();
-                    cur_base = base;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) tap_off[k] = t.off[k];
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    tap_acc[k][0] += t.w[k] * df[0]; tap_acc[k][1] += t.w[k] * df[1];
-                    tap_acc[k][2] += t.w[k] * df[2]; tap_acc[k][3] += t.w[k] * df[3];
-                }
-            }
+            __syncwarp();
         }
         flush();
+        if (dbias_out && lane == 0) {
+#pragma unroll
+            for (int hd = 0; hd < HEADS; ++hd) dbias_out[((size_t)n * HEADS + hd) * P.OV + ov] = dbias_acc[hd];
+        }
         // dpq[h][j] += sum_s ds[s][h] pe[s][j]
         {
             const int total = HEADS * P.npe;
@@ -431,7 +505,7 @@ k_epi_attn_bwd(EpiParams P, int n_queries, const float *__restrict__ lse, const 
                 if (o < total) {
                     const int hd = o / P.npe, j = o % P.npe;
                     float acc = 0.0f;
-                    for (int s = 0; s < 32; ++s) acc += sm.ds[s][hd] * sm.pe[s][j];
+                    for (int s = 0; s < 32; ++s) acc += sm.ds_all[s][hd] * sm.pe[s][j];
                     dpq_acc[i] += acc;
                 }
             }
@@ -452,16 +526,18 @@ k_epi_attn_bwd(EpiParams P, int n_queries, const float *__restrict__ lse, const 
     }
 }
 
+constexpr int kEpiSubFwd = 8, kEpiSubBwd = 4;
+
 template <int HEADS>
 static int launch_epi(bool backward, const EpiParams &P, int n, float *z, float *e, float *mass, float *lse_out,
                       const float *lse, const float *dz, const float *de, const float *dmass, const float *Drow,
                       float *dqt, float *dpq, float *dbias, float *dfeat, cudaStream_t st) {
     const int blocks = (n + kEpiWarps - 1) / kEpiWarps;
     if (!backward) {
-        k_epi_attn_fwd<HEADS><<<blocks, kEpiWarps * 32, 0, st>>>(P, n, z, e, mass, lse_out);
+        k_epi_attn_fwd<HEADS, kEpiSubFwd><<<blocks, kEpiWarps * 32, 0, st>>>(P, n, z, e, mass, lse_out);
         PS_LAUNCH_CHECK("k_epi_attn_fwd");
     } else {
-        k_epi_attn_bwd<HEADS><<<blocks, kEpiWarps * 32, 0, st>>>(P, n, lse, dz, de, dmass, Drow, dqt, dpq, dbias, dfeat);
+        k_epi_attn_bwd<HEADS, kEpiSubBwd><<<blocks, kEpiWarps * 32, 0, st>>>(P, n, lse, dz, de, dmass, Drow, dqt, dpq, dbias, dfeat);
         PS_LAUNCH_CHECK("k_epi_attn_bwd");
     }
     return PS_OK;

@@ -36,6 +36,15 @@ struct ImageState {
     float4 *run_state;        // [S*V*(kMaxSegments-1)*H*W] (T, Cr, Cg, Cb) in front of list runs 1.. (segK > 1)
 };
 
+// Fused loss epilogue of the compositor: squared error against a target image summed per
+// view in the forward, dL/dC = grad_scale[view] (C - target) formed inside the backward.  All null = off.
+constexpr int kLossSlots = PS_LOSS_SLOTS;
+struct LossEpilogue {
+    const float *target;       // [S*V, 3, H, W]
+    float *sums;               // forward: [S*V, 2, kLossSlots] partial sums (raw, clipped), zeroed by the caller
+    const float *grad_scale;   // backward: [S*V]
+};
+
 constexpr int kMaxSegments = 4;   // list runs per warp task (raster_composite2.cu)
 
 struct Dims {
@@ -108,10 +117,10 @@ int launch_binning(const Dims &d, const Geom &g, unsigned long long *keys,
                    unsigned long long *keys_alt, int sort_impl, int segment_hint, cudaStream_t st);
 int launch_composite_forward(const Dims &d, const Inputs &in, const Geom &g,
                              const unsigned long long *keys, const ImageState &img,
-                             float *out_color, cudaStream_t st);
+                             float *out_color, const LossEpilogue &loss, cudaStream_t st);
 int launch_composite_backward(const Dims &d, const Inputs &in, const Geom &g,
                               const unsigned long long *keys, const ImageState &img,
-                              const float *d_color, const ViewGrads &vg, cudaStream_t st);
+                              const float *d_color, const ViewGrads &vg, const LossEpilogue &loss, cudaStream_t st);
 // legacy CTA-per-tile compositor (round 1), kept selectable for A/B measurements
 int launch_composite_forward_v1(const Dims &d, const Inputs &in, const Geom &g,
                                 const unsigned long long *keys, const ImageState &img,

@@ -282,14 +282,24 @@ PS_API int ps_raster_layout_query(const ps_raster_desc *desc, ps_raster_layout *
     return PS_OK;
 }
 
-PS_API int ps_raster_forward(const ps_raster_desc *desc, const ps_raster_inputs *in, const ps_raster_state *state,
-                      float *out_color, int32_t *out_radii, int64_t *n_instances_host, void *stream) {
+}  // extern "C"
+
+static int raster_forward_impl(const ps_raster_desc *desc, const ps_raster_inputs *in, const ps_raster_state *state,
+                               float *out_color, int32_t *out_radii, int64_t *n_instances_host,
+                               const ps_raster_loss *loss, void *stream) {
     int rc = validate(desc);
     if (rc) return rc;
     const Layout L = make_layout(desc);
     rc = check_common(desc, in, state, L);
     if (rc) return rc;
-    if (!out_color) { set_error("out_color is NULL"); return PS_ERR_INVALID_ARGUMENT; }
+    LossEpilogue le{nullptr, nullptr, nullptr};
+    if (loss) {
+        if (!loss->target || !loss->sums) { set_error("ps_raster_loss: target / sums is NULL"); return PS_ERR_INVALID_ARGUMENT; }
+        le.target = loss->target; le.sums = loss->sums;
+    } else if (!out_color) {
+        set_error("out_color is NULL");
+        return PS_ERR_INVALID_ARGUMENT;
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Dims d = make_dims(desc);
     const Inputs I = make_inputs(in);
@@ -315,7 +325,9 @@ PS_API int ps_raster_forward(const ps_raster_desc *desc, const ps_raster_inputs 
     PS_CUDA_CHECK(cudaStreamWaitEvent(st, sc->join, 0));   // join
     if (n_instances_host)
         PS_CUDA_CHECK(cudaMemcpyAsync(n_instances_host, g.n_instances, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    if ((rc = launch_composite_forward(d, I, g, keys, img, out_color, st))) return rc;
+    if (le.sums)
+        PS_CUDA_CHECK(cudaMemsetAsync(le.sums, 0, sizeof(float) * 2 * kLossSlots * (size_t)d.S * d.V, st));
+    if ((rc = launch_composite_forward(d, I, g, keys, img, out_color, le, st))) return rc;
     mark(kMarkCompositeFwd, st);
     if (out_radii)
         PS_CUDA_CHECK(cudaMemcpyAsync(out_radii, g.radii, sizeof(int32_t) * (size_t)d.S * d.V * d.P,
@@ -323,15 +335,35 @@ PS_API int ps_raster_forward(const ps_raster_desc *desc, const ps_raster_inputs 
     return PS_OK;
 }
 
-PS_API int ps_raster_backward(const ps_raster_desc *desc, const ps_raster_inputs *in, const ps_raster_state *state,
-                       const float *d_color, void *scratch, size_t scratch_bytes,
-                       const ps_raster_grads *grads, void *stream) {
+extern "C" {
+
+PS_API int ps_raster_forward(const ps_raster_desc *desc, const ps_raster_inputs *in, const ps_raster_state *state,
+                             float *out_color, int32_t *out_radii, int64_t *n_instances_host, void *stream) {
+    return raster_forward_impl(desc, in, state, out_color, out_radii, n_instances_host, nullptr, stream);
+}
+
+PS_API int ps_raster_forward_loss(const ps_raster_desc *desc, const ps_raster_inputs *in, const ps_raster_state *state,
+                                  const ps_raster_loss *loss, float *out_color, int32_t *out_radii,
+                                  int64_t *n_instances_host, void *stream) {
+    if (!loss) { set_error("ps_raster_forward_loss: loss is NULL"); return PS_ERR_INVALID_ARGUMENT; }
+    return raster_forward_impl(desc, in, state, out_color, out_radii, n_instances_host, loss, stream);
+}
+
+}  // extern "C"
+
+static int raster_backward_impl(const ps_raster_desc *desc, const ps_raster_inputs *in, const ps_raster_state *state,
+                                const float *d_color, const float *target, const float *grad_scale, void *scratch,
+                                size_t scratch_bytes, const ps_raster_grads *grads, void *stream) {
     int rc = validate(desc);
     if (rc) return rc;
     const Layout L = make_layout(desc);
     rc = check_common(desc, in, state, L);
     if (rc) return rc;
-    if (!d_color || !scratch || !grads) { set_error("d_color/scratch/grads is NULL"); return PS_ERR_INVALID_ARGUMENT; }
+    if ((!d_color && !(target && grad_scale)) || !scratch || !grads) {
+        set_error("d_color (or target + grad_scale) / scratch / grads is NULL");
+        return PS_ERR_INVALID_ARGUMENT;
+    }
+    const LossEpilogue le{d_color ? nullptr : target, nullptr, d_color ? nullptr : grad_scale};
     if (!grads->d_means || !grads->d_cov || !grads->d_opacities || !grads->d_sh) {
         set_error("a required gradient pointer is NULL");
         return PS_ERR_INVALID_ARGUMENT;
@@ -363,12 +395,28 @@ PS_API int ps_raster_backward(const ps_raster_desc *desc, const ps_raster_inputs
     PS_CUDA_CHECK(cudaEventRecord(sc->join, sc->side));
     PS_CUDA_CHECK(cudaMemsetAsync(scratch, 0, L.sizes.backward_bytes, st));
     mark(kMarkBwdZero, st);
-    if ((rc = launch_composite_backward(d, I, g, keys, img, d_color, vg, st))) return rc;
+    if ((rc = launch_composite_backward(d, I, g, keys, img, d_color, vg, le, st))) return rc;
     mark(kMarkCompositeBwd, st);
     PS_CUDA_CHECK(cudaStreamWaitEvent(st, sc->join, 0));   // join
     if ((rc = launch_preprocess_backward(d, I, g, vg, *grads, st))) return rc;
     mark(kMarkPreprocessBwd, st);
     return PS_OK;
+}
+
+extern "C" {
+
+PS_API int ps_raster_backward(const ps_raster_desc *desc, const ps_raster_inputs *in, const ps_raster_state *state,
+                              const float *d_color, void *scratch, size_t scratch_bytes,
+                              const ps_raster_grads *grads, void *stream) {
+    if (!d_color) { set_error("d_color is NULL"); return PS_ERR_INVALID_ARGUMENT; }
+    return raster_backward_impl(desc, in, state, d_color, nullptr, nullptr, scratch, scratch_bytes, grads, stream);
+}
+
+PS_API int ps_raster_backward_loss(const ps_raster_desc *desc, const ps_raster_inputs *in, const ps_raster_state *state,
+                                   const float *target, const float *grad_scale, void *scratch, size_t scratch_bytes,
+                                   const ps_raster_grads *grads, void *stream) {
+    if (!target || !grad_scale) { set_error("target / grad_scale is NULL"); return PS_ERR_INVALID_ARGUMENT; }
+    return raster_backward_impl(desc, in, state, nullptr, target, grad_scale, scratch, scratch_bytes, grads, stream);
 }
 
 }  // extern "C"

@@ -233,6 +233,9 @@ __device__ __forceinline__ int cull_step(CullPipe &p, const Geom &geo, const Tas
 
 // ================================================================================== forward
 constexpr int kFwdWarps = 4;
+#ifndef PS_FWD_MIN_CTAS
+#define PS_FWD_MIN_CTAS 6              // <= 80 registers: 24 resident warps per SM
+#endif
 constexpr float kStopT = 0.0001f;          // upstream: stop once T (1 - alpha) < 1e-4
 constexpr float kStopGuard = 1.01e-4f;     // a run is folded without replay only if T T_k stays above this
 
@@ -301,9 +304,9 @@ __device__ __forceinline__ void fwd_run(const Geom &geo, const TaskGeom &t, cons
 }
 
 template <int K>
-__global__ void __launch_bounds__(kFwdWarps * 32)
+__global__ void __launch_bounds__(kFwdWarps * 32, PS_FWD_MIN_CTAS)
 k_composite_fwd2(Dims d, Geom geo, const float *__restrict__ bg_all, const unsigned long long *__restrict__ keys,
-                 ImageState img, float *__restrict__ out_color) {
+                 ImageState img, float *__restrict__ out_color, LossEpilogue loss) {
     __shared__ HitQueue s_q[kFwdWarps];
     __shared__ float4 s_ct[K > 1 ? kFwdWarps : 1][32];      // a run's (Cr, Cg, Cb, T)
     __shared__ uint32_t s_last[K > 1 ? kFwdWarps : 1][32];   // its last contributor | stopped << 31
@@ -357,6 +360,7 @@ k_composite_fwd2(Dims d, Geom geo, const float *__restrict__ bg_all, const unsig
     } else if (!valid) {
         return;
     }
+    float sse = 0.0f, sse_clip = 0.0f;
     if (t.inside) {
         const size_t o1 = (size_t)t.vid * t.hw + t.pix;
         img.final_T[o1] = px.T;
@@ -364,8 +368,31 @@ k_composite_fwd2(Dims d, Geom geo, const float *__restrict__ bg_all, const unsig
         const float *bg = bg_all + 3 * t.vid;
         const float r = px.Cr + px.T * bg[0], g = px.Cg + px.T * bg[1], b = px.Cb + px.T * bg[2];
         const size_t o3 = (size_t)t.vid * 3 * t.hw + t.pix;
-        out_color[o3] = r; out_color[o3 + t.hw] = g; out_color[o3 + 2 * t.hw] = b;
+        if (out_color) { out_color[o3] = r; out_color[o3 + t.hw] = g; out_color[o3 + 2 * t.hw] = b; }
         img.color[o3] = r; img.color[o3 + t.hw] = g; img.color[o3 + 2 * t.hw] = b;
+        if (loss.target) {
+            // loss epilogue (loss_mse.py:30-31, metrics.py:11-19): squared error of this pixel, raw and clipped
+            const float tr = loss.target[o3], tg = loss.target[o3 + t.hw], tb = loss.target[o3 + 2 * t.hw];
+            const float er = r - tr, eg = g - tg, eb = b - tb;
+            sse = er * er + eg * eg + eb * eb;
+            const float cr = __saturatef(r) - __saturatef(tr), cg = __saturatef(g) - __saturatef(tg),
+                        cb = __saturatef(b) - __saturatef(tb);
+            sse_clip = cr * cr + cg * cg + cb * cb;
+        }
+    }
+    if (loss.target) {
+        // one pair of atomics per warp task, spread over kLossSlots addresses per view
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sse += __shfl_xor_sync(0xffffffffu, sse, o);
+            sse_clip += __shfl_xor_sync(0xffffffffu, sse_clip, o);
+        }
+        if (lane == 0) {
+            const int slot = (int)((blockIdx.x * kTasksPerCta + warp / K) & (kLossSlots - 1));
+            float *dst = loss.sums + ((size_t)t.vid * 2) * kLossSlots + slot;
+            atomicAdd(dst, sse);
+            atomicAdd(dst + kLossSlots, sse_clip);
+        }
     }
 }
 
@@ -468,7 +495,7 @@ __device__ __forceinline__ void bwd_batch(BwdSmem &sm, BwdPixel &px, const TaskG
 template <int K>
 __global__ void __launch_bounds__(kBwdWarps * 32, 6)
 k_composite_bwd2(Dims d, Geom geo, const float *__restrict__ bg_all, const unsigned long long *__restrict__ keys,
-                 ImageState img, const float *__restrict__ d_color, ViewGrads vg) {
+                 ImageState img, const float *__restrict__ d_color, ViewGrads vg, LossEpilogue loss) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     constexpr int kTasksPerCta = kBwdWarps / K;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -484,8 +511,16 @@ k_composite_bwd2(Dims d, Geom geo, const float *__restrict__ bg_all, const unsig
     if (t.inside) {
         const size_t o1 = (size_t)t.vid * t.hw + t.pix, o3 = (size_t)t.vid * 3 * t.hw + t.pix;
         px.last = img.n_contrib[o1];
-        px.dpr = d_color[o3]; px.dpg = d_color[o3 + t.hw]; px.dpb = d_color[o3 + 2 * t.hw];
-        px.Q = img.color[o3] * px.dpr + img.color[o3 + t.hw] * px.dpg + img.color[o3 + 2 * t.hw] * px.dpb;
+        const float c_r = img.color[o3], c_g = img.color[o3 + t.hw], c_b = img.color[o3 + 2 * t.hw];
+        if (d_color) {
+            px.dpr = d_color[o3]; px.dpg = d_color[o3 + t.hw]; px.dpb = d_color[o3 + 2 * t.hw];
+        } else {
+            // fused loss: dL/dC = scale[view] * (C - target), never materialised as a tensor
+            const float sc = loss.grad_scale[t.vid];
+            px.dpr = sc * (c_r - loss.target[o3]); px.dpg = sc * (c_g - loss.target[o3 + t.hw]);
+            px.dpb = sc * (c_b - loss.target[o3 + 2 * t.hw]);
+        }
+        px.Q = c_r * px.dpr + c_g * px.dpg + c_b * px.dpb;
     }
     sm.dp[lane] = make_float4(px.dpr, px.dpg, px.dpb, 0.0f);
     // nothing beyond the block's last contributor; the run split is the forward's (on the full count)
@@ -545,27 +580,31 @@ int set_composite_option(int which, int value) {
 
 template <int K>
 static int launch_fwd(const Dims &d, const Inputs &in, const Geom &g, const unsigned long long *keys,
-                      const ImageState &img, float *out_color, cudaStream_t st) {
+                      const ImageState &img, float *out_color, const LossEpilogue &loss, cudaStream_t st) {
     const long long tasks = (long long)d.S * d.V * d.tiles * 8;
     constexpr int per_cta = kFwdWarps / K;
-    k_composite_fwd2<K><<<(unsigned)((tasks + per_cta - 1) / per_cta), kFwdWarps * 32, 0, st>>>(d, g, in.bg, keys, img, out_color);
+    k_composite_fwd2<K><<<(unsigned)((tasks + per_cta - 1) / per_cta), kFwdWarps * 32, 0, st>>>(d, g, in.bg, keys, img, out_color, loss);
     PS_LAUNCH_CHECK("k_composite_fwd2");
     return PS_OK;
 }
 
 int launch_composite_forward(const Dims &d, const Inputs &in, const Geom &g, const unsigned long long *keys,
-                             const ImageState &img, float *out_color, cudaStream_t st) {
-    if (composite_impl() == 1) return launch_composite_forward_v1(d, in, g, keys, img, out_color, st);
+                             const ImageState &img, float *out_color, const LossEpilogue &loss, cudaStream_t st) {
+    if (composite_impl() == 1) {
+        if (loss.target || !out_color) { set_error("the legacy compositor has no loss epilogue"); return PS_ERR_UNSUPPORTED; }
+        return launch_composite_forward_v1(d, in, g, keys, img, out_color, st);
+    }
     switch (d.segK) {
-        case 4: return launch_fwd<4>(d, in, g, keys, img, out_color, st);
-        case 2: return launch_fwd<2>(d, in, g, keys, img, out_color, st);
-        default: return launch_fwd<1>(d, in, g, keys, img, out_color, st);
+        case 4: return launch_fwd<4>(d, in, g, keys, img, out_color, loss, st);
+        case 2: return launch_fwd<2>(d, in, g, keys, img, out_color, loss, st);
+        default: return launch_fwd<1>(d, in, g, keys, img, out_color, loss, st);
     }
 }
 
 template <int K>
 static int launch_bwd(const Dims &d, const Inputs &in, const Geom &g, const unsigned long long *keys,
-                      const ImageState &img, const float *d_color, const ViewGrads &vg, cudaStream_t st) {
+                      const ImageState &img, const float *d_color, const ViewGrads &vg, const LossEpilogue &loss,
+                      cudaStream_t st) {
     const long long tasks = (long long)d.S * d.V * d.tiles * 8;
     constexpr int per_cta = kBwdWarps / K;
     const size_t smem = sizeof(BwdSmem) * kBwdWarps;
@@ -573,18 +612,22 @@ static int launch_bwd(const Dims &d, const Inputs &in, const Geom &g, const unsi
     if (first_use_on_device(attr_devices)) {
         PS_CUDA_CHECK(cudaFuncSetAttribute(k_composite_bwd2<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    k_composite_bwd2<K><<<(unsigned)((tasks + per_cta - 1) / per_cta), kBwdWarps * 32, smem, st>>>(d, g, in.bg, keys, img, d_color, vg);
+    k_composite_bwd2<K><<<(unsigned)((tasks + per_cta - 1) / per_cta), kBwdWarps * 32, smem, st>>>(d, g, in.bg, keys, img, d_color, vg, loss);
     PS_LAUNCH_CHECK("k_composite_bwd2");
     return PS_OK;
 }
 
 int launch_composite_backward(const Dims &d, const Inputs &in, const Geom &g, const unsigned long long *keys,
-                              const ImageState &img, const float *d_color, const ViewGrads &vg, cudaStream_t st) {
-    if (composite_impl() == 1) return launch_composite_backward_v1(d, in, g, keys, img, d_color, vg, st);
+                              const ImageState &img, const float *d_color, const ViewGrads &vg,
+                              const LossEpilogue &loss, cudaStream_t st) {
+    if (composite_impl() == 1) {
+        if (!d_color) { set_error("the legacy compositor has no loss epilogue"); return PS_ERR_UNSUPPORTED; }
+        return launch_composite_backward_v1(d, in, g, keys, img, d_color, vg, st);
+    }
     switch (d.segK) {
-        case 4: return launch_bwd<4>(d, in, g, keys, img, d_color, vg, st);
-        case 2: return launch_bwd<2>(d, in, g, keys, img, d_color, vg, st);
-        default: return launch_bwd<1>(d, in, g, keys, img, d_color, vg, st);
+        case 4: return launch_bwd<4>(d, in, g, keys, img, d_color, vg, loss, st);
+        case 2: return launch_bwd<2>(d, in, g, keys, img, d_color, vg, loss, st);
+        default: return launch_bwd<1>(d, in, g, keys, img, d_color, vg, loss, st);
     }
 }
 

@@ -19,7 +19,7 @@ constexpr int kPreBwdThreads = 128;
 // launch_gradient_fill (plain memsets, issued on a side stream so that they overlap the
 // compute-bound composite backward).  SH rows are staged per warp in shared memory: coefficients
 // come in with coalesced row-wise loads, dL/dSH goes out the same way.
-__global__ void __launch_bounds__(kPreBwdThreads, 4)
+__global__ void __launch_bounds__(kPreBwdThreads, 5)
 k_preprocess_bwd(Dims d, Inputs in, Geom geo, ViewGrads vgr, ps_raster_grads out, int row_stride) {
     extern __shared__ float s_dsh[];   // [warps][32][row_stride] coefficients (V == 1: reused for the gradient)
     if (*geo.n_instances > d.capacity) return;

@@ -19,7 +19,7 @@ import torch
 from torch import Tensor
 
 from .. import _lib
-from ..rasterizer import rasterize_gaussians
+from ..rasterizer import rasterize_gaussians, rasterize_gaussians_mse
 
 DepthRenderingMode = Literal["depth", "disparity", "relative_disparity", "log"]
 
@@ -98,6 +98,29 @@ def render_views(
         image_shape=(h, w), views_per_scene=v, sh_degree=degree, use_sh=use_sh, sh_layout=layout,
         scene_scale=cams["scene_scale"] if scale_invariant else None, state_out=state_out)
     return color.reshape(s, v, 3, h, w)
+
+
+def render_views_mse(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple[int, int],
+                     background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
+                     gaussian_sh_coefficients: Tensor, gaussian_opacities: Tensor, target: Tensor,
+                     scale_invariant: bool = True, want_color: bool = True):
+    """render_views with the loss epilogue fused into the compositor: `target`
+    [s, v, 3, h, w] -> (sse [s, v] differentiable sum of squared errors, sse_clipped [s, v] the same on images
+    clipped to [0, 1] (what compute_psnr needs), color [s, v, 3, h, w] detached or None).  See
+    pixelsplat_b200/loss.py for the LossMse / PSNR built on top."""
+    s, v = extrinsics.shape[:2]
+    n = gaussian_sh_coefficients.shape[-1]
+    cams = camera_setup(extrinsics.reshape(s * v, 4, 4), intrinsics.reshape(s * v, 3, 3),
+                        near.reshape(s * v), far.reshape(s * v), scale_invariant)
+    h, w = image_shape
+    sse, sse_clipped, color, _ = rasterize_gaussians_mse(
+        gaussian_means, gaussian_covariances, gaussian_opacities, gaussian_sh_coefficients,
+        target.reshape(s * v, 3, h, w).to(torch.float32),
+        viewmatrix=cams["viewmatrix"], projmatrix=cams["projmatrix"], campos=cams["campos"],
+        tanfov=cams["tanfov"], background=background_color.reshape(s * v, 3).to(torch.float32),
+        image_shape=(h, w), views_per_scene=v, sh_degree=isqrt(n) - 1, use_sh=True, sh_layout=_lib.PS_SH_3M,
+        scene_scale=cams["scene_scale"] if scale_invariant else None, want_color=want_color)
+    return sse.reshape(s, v), sse_clipped.reshape(s, v), (color.reshape(s, v, 3, h, w) if want_color else None)
 
 
 def render_cuda(

@@ -10,7 +10,7 @@ from typing import Any, Literal, Optional
 import torch
 from torch import Tensor, nn
 
-from .cuda_splatting import DepthRenderingMode, render_depth_views, render_views
+from .cuda_splatting import DepthRenderingMode, render_depth_views, render_views, render_views_mse
 
 
 @dataclass
@@ -54,6 +54,17 @@ class DecoderSplattingCUDA(nn.Module):
                              gaussians.covariances, gaussians.harmonics, gaussians.opacities)
         return DecoderOutput(color, None if depth_mode is None else self.render_depth(
             gaussians, extrinsics, intrinsics, near, far, image_shape, depth_mode))
+
+    def forward_mse(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
+                    image_shape: tuple[int, int], target: Tensor, want_color: bool = True):
+        """`forward` with LossMse / PSNR sums taken in the compositor's epilogue (row f-4):
+        -> (DecoderOutput (color detached, or None when want_color=False), sse [b, v], sse_clipped [b, v]).
+        pixelsplat_b200.loss.mse_from_sse / psnr_from_sse turn the sums into the reference's numbers."""
+        b, v, _, _ = extrinsics.shape
+        sse, sse_clipped, color = render_views_mse(
+            extrinsics, intrinsics, near, far, image_shape, self.background_color.expand(b, v, 3), gaussians.means,
+            gaussians.covariances, gaussians.harmonics, gaussians.opacities, target, want_color=want_color)
+        return DecoderOutput(color, None), sse, sse_clipped
 
     def render_depth(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor,
                      far: Tensor, image_shape: tuple[int, int],

@@ -33,6 +33,7 @@ from .sh import convention_id
 #              if it had overflowed.  Forwards with no backward coming (inference) are always checked
 #              synchronously, so a truncated image is never returned silently.
 _CHECK_MODE = os.environ.get("PIXELSPLAT_B200_CAPACITY_CHECK", "sync")
+_HEADROOM = 1.25        # capacity kept for the next call of a shape = headroom x the instances it needed
 _capacity_hint: dict[tuple, int] = {}
 _segment_hint: dict[tuple, int] = {}
 _pending: dict[tuple, "weakref.ref"] = {}       # last deferred (unverified) state per shape key
@@ -54,6 +55,17 @@ def set_capacity_check(mode: str) -> None:
     if mode not in ("sync", "deferred"):
         raise ValueError("mode must be 'sync' or 'deferred'")
     _CHECK_MODE = mode
+
+
+def set_capacity_headroom(factor: float) -> None:
+    """Head-room factor (>= 1) applied to the instance count a forward needed when sizing the binning buffers of
+    the NEXT forward of the same shape (default 1.25).  A step captured into a CUDA graph freezes its capacity,
+    so a training loop whose Gaussians move between replays should capture with a generous factor (the count is
+    still checked after every replay: `RasterOutputState.verify`)."""
+    global _HEADROOM
+    if not factor >= 1.0:
+        raise ValueError("headroom factor must be >= 1")
+    _HEADROOM = float(factor)
 
 
 def set_sh_basis(convention) -> None:
@@ -131,7 +143,7 @@ class RasterOutputState:
         n = self.num_instances()
         if n > self.desc.instance_capacity:
             if self.hint_key is not None:
-                _capacity_hint[self.hint_key] = int(n * 1.25) + 4096
+                _capacity_hint[self.hint_key] = int(n * _HEADROOM) + 4096
             raise RuntimeError(
                 f"rasterizer binning overflow: {n} instances needed, capacity was "
                 f"{self.desc.instance_capacity}; the forward result of this call is invalid. "
@@ -180,15 +192,17 @@ def _make_desc(S, V, P, M, deg, sh_layout, cov_layout, H, W, capacity, sort_impl
 
 
 def _forward_native(means, cov, opac, sh, cams, S, V, P, M, deg, sh_layout, cov_layout, H, W,
-                    sort_impl, want_radii, sh_basis=0, backward_follows=False):
+                    sort_impl, want_radii, sh_basis=0, backward_follows=False, loss_target=None, want_color=True):
+    """Returns (color | None, radii | None, state) and, with `loss_target`, a 4th element: the
+    [S*V, 2, LOSS_SLOTS] partial sums of the fused loss epilogue."""
     dev = means.device
     with torch.cuda.device(dev):            # the library works on the CURRENT device
         return _forward_on_device(means, cov, opac, sh, cams, S, V, P, M, deg, sh_layout, cov_layout, H, W,
-                                  sort_impl, want_radii, sh_basis, backward_follows)
+                                  sort_impl, want_radii, sh_basis, backward_follows, loss_target, want_color)
 
 
 def _forward_on_device(means, cov, opac, sh, cams, S, V, P, M, deg, sh_layout, cov_layout, H, W,
-                       sort_impl, want_radii, sh_basis, backward_follows):
+                       sort_impl, want_radii, sh_basis, backward_follows, loss_target=None, want_color=True):
     dev = means.device
     key = (dev.index, S, V, P, H, W)
     capturing = torch.cuda.is_current_stream_capturing()
@@ -208,8 +222,10 @@ def _forward_on_device(means, cov, opac, sh, cams, S, V, P, M, deg, sh_layout, c
         geom = torch.empty(sz.geom_bytes, dtype=torch.uint8, device=dev)
         binning = torch.empty(sz.binning_bytes, dtype=torch.uint8, device=dev)
         image = torch.empty(sz.image_bytes, dtype=torch.uint8, device=dev)
-        color = torch.empty((S * V, 3, H, W), dtype=torch.float32, device=dev)
+        color = torch.empty((S * V, 3, H, W), dtype=torch.float32, device=dev) if want_color else None
         radii = torch.empty((S * V, P), dtype=torch.int32, device=dev) if want_radii else None
+        sums = (torch.empty((S * V, 2, _lib.LOSS_SLOTS), dtype=torch.float32, device=dev)
+                if loss_target is not None else None)
         n_host = _pinned_slot()
         inputs = _lib.RasterInputs(
             means.data_ptr(), cov.data_ptr(), opac.data_ptr(), sh.data_ptr(),
@@ -218,30 +234,39 @@ def _forward_on_device(means, cov, opac, sh, cams, S, V, P, M, deg, sh_layout, c
             cams["scene_scale"].data_ptr() if cams.get("scene_scale") is not None else None)
         state = _lib.RasterState(geom.data_ptr(), geom.numel(), binning.data_ptr(), binning.numel(),
                                  image.data_ptr(), image.numel())
-        rc = _lib.lib.ps_raster_forward(ctypes.byref(desc), ctypes.byref(inputs), ctypes.byref(state),
-                                        _ptr(color), _ptr(radii), ctypes.c_void_p(n_host.data_ptr()),
-                                        ctypes.c_void_p(stream.cuda_stream))
-        _lib.check(rc, "ps_raster_forward")
+        if loss_target is None:
+            rc = _lib.lib.ps_raster_forward(ctypes.byref(desc), ctypes.byref(inputs), ctypes.byref(state),
+                                            _ptr(color), _ptr(radii), ctypes.c_void_p(n_host.data_ptr()),
+                                            ctypes.c_void_p(stream.cuda_stream))
+            _lib.check(rc, "ps_raster_forward")
+            ret = lambda st_: (color, radii, st_)
+        else:
+            loss = _lib.RasterLoss(loss_target.data_ptr(), sums.data_ptr())
+            rc = _lib.lib.ps_raster_forward_loss(ctypes.byref(desc), ctypes.byref(inputs), ctypes.byref(state),
+                                                 ctypes.byref(loss), _ptr(color), _ptr(radii),
+                                                 ctypes.c_void_p(n_host.data_ptr()), ctypes.c_void_p(stream.cuda_stream))
+            _lib.check(rc, "ps_raster_forward_loss")
+            ret = lambda st_: (color, radii, st_, sums)
         if torch.cuda.is_current_stream_capturing():
             # CUDA-graph capture: shapes and capacity are frozen into the graph; the count still
             # lands in pinned memory on every replay and is checked by the caller afterwards
             if key not in _capacity_hint:
                 raise RuntimeError("run this shape once eagerly before capturing it in a CUDA graph "
                                    "(the binning capacity must be known)")
-            return color, radii, RasterOutputState(desc, geom, binning, image, n_host, None, key)
+            return ret(RasterOutputState(desc, geom, binning, image, n_host, None, key))
         event = torch.cuda.Event()
         event.record(stream)
         st = RasterOutputState(desc, geom, binning, image, n_host, event, key)
         if _CHECK_MODE == "deferred" and key in _capacity_hint and backward_follows:
             _pending[key] = weakref.ref(st)
-            return color, radii, st
+            return ret(st)
         n = st.num_instances()
         if n <= capacity:
             st.verified = True
             # keep ~25 % head-room for the next call of the same shape
-            _capacity_hint[key] = max(_capacity_hint.get(key, 0), int(n * 1.25) + 4096)
-            return color, radii, st
-        capacity = int(n * 1.25) + 4096
+            _capacity_hint[key] = max(_capacity_hint.get(key, 0), int(n * _HEADROOM) + 4096)
+            return ret(st)
+        capacity = int(n * _HEADROOM) + 4096
         _capacity_hint[key] = capacity
 
 
@@ -321,6 +346,72 @@ def rasterize_gaussians(
 ) -> tuple[Tensor, Tensor]:
     """Batched differentiable rasterization: S scenes x V views in one set of launches.
     Returns (color [S*V, 3, H, W], radii [S*V, P] int32)."""
+    means, covariances, opacities, colors, cams, S, V, P, M, cov_layout, H, W = _prepare(
+        means, covariances, opacities, colors, viewmatrix, projmatrix, campos, tanfov, background, image_shape,
+        views_per_scene, use_sh, sh_layout, scene_scale)
+    VT = S * V
+    if means2d is not None and tuple(means2d.shape) != (VT, P, 3):
+        raise ValueError(f"means2d must be [S*V, P, 3], got {tuple(means2d.shape)}")
+    return _RasterizeFn.apply(means, covariances, opacities, colors, means2d, cams, S, V, P, M,
+                              int(sh_degree), sh_layout, cov_layout, int(H), int(W), int(sort_impl),
+                              state_out, _SH_BASIS if sh_basis is None else convention_id(sh_basis))
+
+
+class _RasterizeMseFn(torch.autograd.Function):
+    """Rasterize + squared error against a target in one pass.  Differentiable output:
+    sse [S*V] = sum over the view's pixels and channels of (C - target)^2; its gradient g [S*V] reaches the
+    composite backward as the per-view scale 2 g of (C - target), formed in-kernel."""
+
+    @staticmethod
+    def forward(ctx, means, cov, opac, sh, target, cams, S, V, P, M, deg, sh_layout, cov_layout, H, W, sort_impl,
+                state_out, sh_basis, want_color):
+        backward_follows = any(ctx.needs_input_grad[:4])
+        color, radii, st, sums = _forward_native(means, cov, opac, sh, cams, S, V, P, M, deg, sh_layout, cov_layout,
+                                                 H, W, sort_impl, True, sh_basis, backward_follows,
+                                                 loss_target=target, want_color=want_color)
+        ctx.save_for_backward(means, cov, opac, sh, target)
+        ctx.cams, ctx.st = cams, st
+        if state_out is not None:
+            state_out.append(st)
+        totals = sums.sum(dim=-1)                                    # [S*V, 2]
+        sse, sse_clipped = totals[:, 0].contiguous(), totals[:, 1].contiguous()
+        if color is None:
+            color = torch.empty(0, device=means.device)
+        ctx.mark_non_differentiable(sse_clipped, color, radii)
+        return sse, sse_clipped, color, radii
+
+    @staticmethod
+    def backward(ctx, d_sse, _d_clip, _d_color, _d_radii):
+        means, cov, opac, sh, target = ctx.saved_tensors
+        st: RasterOutputState = ctx.st
+        st.verify()
+        desc, cams = st.desc, ctx.cams
+        dev = means.device
+        scale = (2.0 * d_sse).to(torch.float32).contiguous()
+        sz = _lib.sizes(desc)
+        scratch = torch.empty(sz.backward_bytes, dtype=torch.uint8, device=dev)
+        d_means, d_cov = torch.empty_like(means), torch.empty_like(cov)
+        d_opac, d_sh = torch.empty_like(opac), torch.empty_like(sh)
+        inputs = _lib.RasterInputs(
+            means.data_ptr(), cov.data_ptr(), opac.data_ptr(), sh.data_ptr(),
+            cams["viewmatrix"].data_ptr(), cams["projmatrix"].data_ptr(), cams["campos"].data_ptr(),
+            cams["tanfov"].data_ptr(), cams["background"].data_ptr(),
+            cams["scene_scale"].data_ptr() if cams.get("scene_scale") is not None else None)
+        grads = _lib.RasterGrads(d_means.data_ptr(), d_cov.data_ptr(), d_opac.data_ptr(), d_sh.data_ptr(), None)
+        state = st.raw_state()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            rc = _lib.lib.ps_raster_backward_loss(ctypes.byref(desc), ctypes.byref(inputs), ctypes.byref(state),
+                                                  ctypes.c_void_p(target.data_ptr()), ctypes.c_void_p(scale.data_ptr()),
+                                                  ctypes.c_void_p(scratch.data_ptr()), scratch.numel(),
+                                                  ctypes.byref(grads), ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "ps_raster_backward_loss")
+        return (d_means, d_cov, d_opac, d_sh) + (None,) * 15
+
+
+def _prepare(means, covariances, opacities, colors, viewmatrix, projmatrix, campos, tanfov, background, image_shape,
+             views_per_scene, use_sh, sh_layout, scene_scale):
+    """Argument checks shared by rasterize_gaussians and rasterize_gaussians_mse."""
     if means.dim() != 3 or means.shape[-1] != 3:
         raise ValueError(f"means must be [S, P, 3], got {tuple(means.shape)}")
     S, P, _ = means.shape
@@ -352,11 +443,23 @@ def rasterize_gaussians(
         background=_req(background, "background", (VT, 3)),
         scene_scale=None if scene_scale is None else _req(scene_scale, "scene_scale", (VT,)),
     )
-    if means2d is not None and tuple(means2d.shape) != (VT, P, 3):
-        raise ValueError(f"means2d must be [S*V, P, 3], got {tuple(means2d.shape)}")
-    return _RasterizeFn.apply(means, covariances, opacities, colors, means2d, cams, S, V, P, M,
-                              int(sh_degree), sh_layout, cov_layout, int(H), int(W), int(sort_impl),
-                              state_out, _SH_BASIS if sh_basis is None else convention_id(sh_basis))
+    return means, covariances, opacities, colors, cams, S, V, P, M, cov_layout, int(H), int(W)
+
+
+def rasterize_gaussians_mse(means: Tensor, covariances: Tensor, opacities: Tensor, colors: Tensor, target: Tensor, *,
+                            viewmatrix: Tensor, projmatrix: Tensor, campos: Tensor, tanfov: Tensor, background: Tensor,
+                            image_shape: tuple[int, int], views_per_scene: int, sh_degree: int, use_sh: bool = True,
+                            sh_layout: int = PS_SH_M3, scene_scale: Optional[Tensor] = None, sort_impl: int = 0,
+                            state_out: Optional[list] = None, sh_basis=None, want_color: bool = True):
+    """rasterize_gaussians + the loss epilogue: returns (sse [S*V] differentiable, sse_clipped [S*V], color
+    [S*V, 3, H, W] detached (empty when want_color=False), radii).  `target` is [S*V, 3, H, W]."""
+    means, covariances, opacities, colors, cams, S, V, P, M, cov_layout, H, W = _prepare(
+        means, covariances, opacities, colors, viewmatrix, projmatrix, campos, tanfov, background, image_shape,
+        views_per_scene, use_sh, sh_layout, scene_scale)
+    target = _req(target, "target", (S * V, 3, H, W))
+    return _RasterizeMseFn.apply(means, covariances, opacities, colors, target, cams, S, V, P, M, int(sh_degree),
+                                 sh_layout, cov_layout, H, W, int(sort_impl), state_out,
+                                 _SH_BASIS if sh_basis is None else convention_id(sh_basis), bool(want_color))
 
 
 # ------------------------------------------------------------------ drop-in extension surface

@@ -114,3 +114,21 @@ def test_synthetic_scenes_are_deterministic():
     assert abs(float(synthetic.scene_re10k_like(seed=0).near[0]) - 0.2933) < 1e-3
     evals = torch.linalg.eigvalsh(a.covariances)
     assert (evals > 0).all()
+
+
+def test_loss_module_matches_the_reference_formulas():
+    """pixelsplat_b200.loss on CPU tensors (pure torch): LossMse == weight * mean(delta^2), compute_psnr clips to
+    [0, 1] first, and the from-sums forms give the same numbers (loss_mse.py:30-31, metrics.py:11-19)."""
+    from pixelsplat_b200 import loss as L
+    g = torch.Generator().manual_seed(0)
+    pred = torch.rand(2, 3, 3, 8, 10, generator=g) * 1.5 - 0.25
+    tgt = torch.rand(2, 3, 3, 8, 10, generator=g)
+    m = L.LossMse(L.LossMseCfgWrapper(L.LossMseCfg(0.5)))
+    out = type("O", (), {"color": pred})()
+    want = 0.5 * ((pred - tgt) ** 2).mean()
+    assert torch.allclose(m(out, {"target": {"image": tgt}}), want) and m.name == "mse"
+    sse = ((pred - tgt) ** 2).sum(dim=(2, 3, 4))
+    assert torch.allclose(m.from_sse(sse, (8, 10)), want)
+    psnr = L.compute_psnr(tgt.flatten(0, 1), pred.flatten(0, 1))
+    sse_c = ((pred.clip(0, 1) - tgt.clip(0, 1)) ** 2).sum(dim=(2, 3, 4))
+    assert torch.allclose(L.psnr_from_sse(sse_c, (8, 10)).flatten(), psnr, atol=1e-5)
