@@ -297,6 +297,17 @@ PS_API int ps_self_attention_forward(int32_t n_images, int32_t tokens, int32_t h
                                      const float *qkv, float scale, float *out, int32_t debug_mode,
                                      void *stream);
 
+/* The same forward, additionally saving what the backward needs to rebuild the forward's probabilities bit for
+ * bit: stats [n_images, heads, 256, 2] = (row max * scale * log2 e, 1 / row sum of the TF32-rounded numerators). */
+PS_API int ps_self_attention_forward_stats(int32_t n_images, int32_t tokens, int32_t heads, int32_t dim_head,
+                                           const float *qkv, float scale, float *out, float *stats, void *stream);
+
+/* Backward (tcgen05, TF32 operands, FP32 accumulate; csrc/self_attention_tc_bwd.cu): autograd of the forward
+ * above.  out / d_out [n_images, 256, heads * 128]; d_qkv has qkv's layout and is fully written. */
+PS_API int ps_self_attention_backward(int32_t n_images, int32_t tokens, int32_t heads, int32_t dim_head,
+                                      const float *qkv, const float *out, const float *d_out, const float *stats,
+                                      float scale, float *d_qkv, void *stream);
+
 /* ---- fused GaussianAdapter ----------------------------------------------
  * Replaces /root/reference/src/model/encoder/common/gaussian_adapter.py:48-95 (+ gaussians.py:8-44):
  * per-ray raw network outputs -> world-space Gaussians.  One camera = one (batch, view) pair; every

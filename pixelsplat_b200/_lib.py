@@ -96,7 +96,8 @@ EXPORTS = ("ps_version", "ps_last_error", "ps_raster_sizes_query", "ps_raster_la
            "ps_timing_enable", "ps_timing_read", "ps_epipolar_geometry",
            "ps_epipolar_attention_forward", "ps_epipolar_attention_backward",
            "ps_self_attention_forward", "ps_gaussian_adapter_forward", "ps_gaussian_adapter_backward",
-           "ps_sh_rotation_matrices", "ps_set_option", "ps_raster_forward_loss", "ps_raster_backward_loss")
+           "ps_sh_rotation_matrices", "ps_set_option", "ps_raster_forward_loss", "ps_raster_backward_loss",
+           "ps_self_attention_forward_stats", "ps_self_attention_backward")
 
 
 class NativeLibraryMissing(ImportError):
@@ -142,6 +143,12 @@ def _load() -> ctypes.CDLL:
     lib.ps_self_attention_forward.argtypes = [ctypes.c_int32] * 4 + [ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p,
                                                                       ctypes.c_int32, ctypes.c_void_p]
     lib.ps_self_attention_forward.restype = ctypes.c_int
+    lib.ps_self_attention_forward_stats.argtypes = [ctypes.c_int32] * 4 + [ctypes.c_void_p, ctypes.c_float,
+                                                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.ps_self_attention_forward_stats.restype = ctypes.c_int
+    lib.ps_self_attention_backward.argtypes = [ctypes.c_int32] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_float,
+                                                                                             ctypes.c_void_p, ctypes.c_void_p]
+    lib.ps_self_attention_backward.restype = ctypes.c_int
     lib.ps_gaussian_adapter_forward.argtypes = [P(AdapterDesc), P(AdapterInputs)] + [ctypes.c_void_p] * 6
     lib.ps_gaussian_adapter_forward.restype = ctypes.c_int
     lib.ps_gaussian_adapter_backward.argtypes = [P(AdapterDesc), P(AdapterInputs)] + [ctypes.c_void_p] * 9

@@ -15,6 +15,8 @@
 // The kernel maps (qt, pq, bias) -> (z, e, mass, lse); the small dense projections around it
 // stay GEMMs.  One warp per query; lane l owns channels 4l..4l+3 for the gather and sample l
 // for the soft-max / PE.  C = 128, S <= 32.
+#include <cstdlib>
+
 #include "ps_common.cuh"
 
 namespace ps {
@@ -203,10 +205,24 @@ k_epi_attn_fwd(EpiParams P, int n_queries, float *__restrict__ z_out, float *__r
         const bool ok = P.valid[ray] != 0;
         const float *fmap = P.feat + (size_t)(b * P.V + o_view) * R * kEpiC + 4 * lane;
 
-        // ---- PE half of the scores, lane = sample
+        // ---- PE half of the scores and the bilinear taps, lane = sample
+        Taps my_taps;
+        int my_cell = -0x7ffffffe;
         {
             float pe[kMaxPE];
             const bool has_sample = lane < P.S;
+            if (has_sample && ok) {
+                const float u = ((float)lane + 0.5f) / (float)P.S;
+                const float sx = sg.x + u * (sg.z - sg.x), sy = sg.y + u * (sg.w - sg.y);
+                my_taps = make_taps(sx, sy, P.h, P.w);
+                const float ix = sx * (float)P.w - 0.5f, iy = sy * (float)P.h - 0.5f;
+                const int bx = (int)fminf(fmaxf(floorf(ix), -2.0f), (float)P.w + 1.0f);
+                const int by = (int)fminf(fmaxf(floorf(iy), -2.0f), (float)P.h + 1.0f);
+                my_cell = by * (P.w + 4) + bx;            // the bilinear cell (backward merges samples that share it)
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { my_taps.off[k] = -1; my_taps.w[k] = 0.0f; }
+            }
             positional_encoding(has_sample ? P.rd[ray * P.S + lane] : 0.0f, P.npe, pe);
 #pragma unroll
             for (int j = 0; j < kMaxPE; ++j)
@@ -230,16 +246,15 @@ k_epi_attn_fwd(EpiParams P, int n_queries, float *__restrict__ z_out, float *__r
             for (int i = 0; i < SUB; ++i) {
                 const int s = sub * SUB + i;
                 f[i][0] = f[i][1] = f[i][2] = f[i][3] = 0.0f;
-                if (s < P.S && ok) {
-                    const float u = ((float)s + 0.5f) / (float)P.S;
-                    const Taps t = make_taps(sg.x + u * (sg.z - sg.x), sg.y + u * (sg.w - sg.y), P.h, P.w);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (t.off[k] >= 0) {
-                            const float4 a = ldg4(fmap + t.off[k]);
-                            f[i][0] += t.w[k] * a.x; f[i][1] += t.w[k] * a.y;
-                            f[i][2] += t.w[k] * a.z; f[i][3] += t.w[k] * a.w;
-                        }
+                for (int k = 0; k < 4; ++k) {
+                    // the taps of sample s were formed once, by lane s (every lane needs the same four)
+                    const int off = __shfl_sync(0xffffffffu, my_taps.off[k], s);
+                    const float wk = __shfl_sync(0xffffffffu, my_taps.w[k], s);
+                    if (off >= 0) {
+                        const float4 a = ldg4(fmap + off);
+                        f[i][0] += wk * a.x; f[i][1] += wk * a.y;
+                        f[i][2] += wk * a.z; f[i][3] += wk * a.w;
                     }
                 }
             }
@@ -368,10 +383,24 @@ k_epi_attn_bwd(EpiParams P, int n_queries, const float *__restrict__ lse, const 
         const size_t map_base = (size_t)(b * P.V + o_view) * R * kEpiC + 4 * lane;
         const float *fmap = P.feat + map_base;
 
-        // ---- PE halves of the score and of d a, lane = sample
+        // ---- PE halves of the score and of d a, and the bilinear taps, lane = sample
+        Taps my_taps;
+        int my_cell = -0x7ffffffe;
         {
             float pe[kMaxPE];
             const bool has_sample = lane < P.S;
+            if (has_sample && ok) {
+                const float u = ((float)lane + 0.5f) / (float)P.S;
+                const float sx = sg.x + u * (sg.z - sg.x), sy = sg.y + u * (sg.w - sg.y);
+                my_taps = make_taps(sx, sy, P.h, P.w);
+                const float ix = sx * (float)P.w - 0.5f, iy = sy * (float)P.h - 0.5f;
+                const int bx = (int)fminf(fmaxf(floorf(ix), -2.0f), (float)P.w + 1.0f);
+                const int by = (int)fminf(fmaxf(floorf(iy), -2.0f), (float)P.h + 1.0f);
+                my_cell = by * (P.w + 4) + bx;            // the bilinear cell (backward merges samples that share it)
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { my_taps.off[k] = -1; my_taps.w[k] = 0.0f; }
+            }
             positional_encoding(has_sample ? P.rd[ray * P.S + lane] : 0.0f, P.npe, pe);
 #pragma unroll
             for (int j = 0; j < kMaxPE; ++j)
@@ -415,16 +444,15 @@ k_epi_attn_bwd(EpiParams P, int n_queries, const float *__restrict__ lse, const 
             for (int i = 0; i < SUB; ++i) {
                 const int s = sub * SUB + i;
                 f[i][0] = f[i][1] = f[i][2] = f[i][3] = 0.0f;
-                if (s < P.S && ok) {
-                    const float u = ((float)s + 0.5f) / (float)P.S;
-                    const Taps t = make_taps(sg.x + u * (sg.z - sg.x), sg.y + u * (sg.w - sg.y), P.h, P.w);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (t.off[k] >= 0) {
-                            const float4 a = ldg4(fmap + t.off[k]);
-                            f[i][0] += t.w[k] * a.x; f[i][1] += t.w[k] * a.y;
-                            f[i][2] += t.w[k] * a.z; f[i][3] += t.w[k] * a.w;
-                        }
+                for (int k = 0; k < 4; ++k) {
+                    // the taps of sample s were formed once, by lane s (every lane needs the same four)
+                    const int off = __shfl_sync(0xffffffffu, my_taps.off[k], s);
+                    const float wk = __shfl_sync(0xffffffffu, my_taps.w[k], s);
+                    if (off >= 0) {
+                        const float4 a = ldg4(fmap + off);
+                        f[i][0] += wk * a.x; f[i][1] += wk * a.y;
+                        f[i][2] += wk * a.z; f[i][3] += wk * a.w;
                     }
                 }
             }
@@ -468,14 +496,14 @@ k_epi_attn_bwd(EpiParams P, int n_queries, const float *__restrict__ lse, const 
                     }
                 }
                 if (s < P.S && ok) {
-                    const float u = ((float)s + 0.5f) / (float)P.S;
-                    const float sx = sg.x + u * (sg.z - sg.x), sy = sg.y + u * (sg.w - sg.y);
-                    const Taps t = make_taps(sx, sy, P.h, P.w);
+                    Taps t;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        t.off[k] = __shfl_sync(0xffffffffu, my_taps.off[k], s);
+                        t.w[k] = __shfl_sync(0xffffffffu, my_taps.w[k], s);
+                    }
                     // identify the bilinear cell by its top-left tap position (may be outside)
-                    const float ix = sx * (float)P.w - 0.5f, iy = sy * (float)P.h - 0.5f;
-                    const int bx = (int)fminf(fmaxf(floorf(ix), -2.0f), (float)P.w + 1.0f);
-                    const int by = (int)fminf(fmaxf(floorf(iy), -2.0f), (float)P.h + 1.0f);
-                    const int base = by * (P.w + 4) + bx;
+                    const int base = __shfl_sync(0xffffffffu, my_cell, s);
                     if (base != cur_base) {
                         flush();
                         cur_base = base;
@@ -534,7 +562,13 @@ static int launch_epi(bool backward, const EpiParams &P, int n, float *z, float 
                       float *dqt, float *dpq, float *dbias, float *dfeat, cudaStream_t st) {
     const int blocks = (n + kEpiWarps - 1) / kEpiWarps;
     if (!backward) {
-        k_epi_attn_fwd<HEADS, kEpiSubFwd><<<blocks, kEpiWarps * 32, 0, st>>>(P, n, z, e, mass, lse_out);
+        static int sub_fwd = 0;                       // PIXELSPLAT_B200_EPI_SUB_FWD = 4 | 8 (A/B runs)
+        if (sub_fwd == 0) {
+            const char *e = getenv("PIXELSPLAT_B200_EPI_SUB_FWD");
+            sub_fwd = (e && e[0] == '4') ? 4 : kEpiSubFwd;
+        }
+        if (sub_fwd == 4) k_epi_attn_fwd<HEADS, 4><<<blocks, kEpiWarps * 32, 0, st>>>(P, n, z, e, mass, lse_out);
+        else k_epi_attn_fwd<HEADS, kEpiSubFwd><<<blocks, kEpiWarps * 32, 0, st>>>(P, n, z, e, mass, lse_out);
         PS_LAUNCH_CHECK("k_epi_attn_fwd");
     } else {
         k_epi_attn_bwd<HEADS, kEpiSubBwd><<<blocks, kEpiWarps * 32, 0, st>>>(P, n, lse, dz, de, dmass, Drow, dqt, dpq, dbias, dfeat);

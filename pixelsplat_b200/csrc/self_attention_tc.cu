@@ -20,108 +20,15 @@
 //      16-byte stores to global.
 // No TMA: the tiles are tiny and L2-resident (112 CTAs x 320 KB); the copy is plain ld.global /
 // st.shared followed by a proxy fence.
-#include "ps_common.cuh"
+#include "umma_tf32.cuh"
 
 namespace ps {
-
-constexpr int kSaL = 256;        // tokens per image
-constexpr int kSaD = 128;        // head dimension
-constexpr int kSaThreads = 256;      // warps 0-3: soft-max rows; warps 4-7: V^T staging; all: Q/K staging, epilogue
-constexpr uint32_t kSaTmemCols = 512;
-
-// fp32 -> nearest TF32 (ties away), kept in an fp32 container: the tensor core ignores the low 13
-// mantissa bits, so rounding here instead of letting it truncate halves the operand error and removes its bias.
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-__device__ __forceinline__ float4 to_tf32(float4 v) { return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w)); }
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// K-major, no swizzle: core matrix = 8 rows x 16 bytes (contiguous 128 B); 8-row groups are
-// adjacent (SBO = 128 B), 16-byte K chunks are `lbo` bytes apart.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3fffu);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
-    d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
-    return d;                                // base offset 0, LBO mode 0, layout type 0 (SWIZZLE_NONE)
-}
-
-// kind::tf32 instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3, M >> 4.
-__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
-        :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint32_t bar_saddr) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar_saddr) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint32_t bar_saddr, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(done) : "r"(bar_saddr), "r"(parity) : "memory");
-    }
-}
-
-// 32 consecutive TMEM columns of this thread's lane -> registers (and back).
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
-    uint32_t r[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
-        :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-           "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
 
 // debug_mode: 0 = attention output; 1 = write the raw logits S = Q K^T instead (`out` is then
 // [n_img, H, 256, 256]) -- used by the tests to isolate the first MMA stage.
 __global__ void __launch_bounds__(kSaThreads, 1)
-k_self_attention_tc(const float *__restrict__ qkv, float *__restrict__ out, int n_heads, float scale_log2e,
-                    int debug_mode) {
+k_self_attention_tc(const float *__restrict__ qkv, float *__restrict__ out, float *__restrict__ stats, int n_heads,
+                    float scale_log2e, int debug_mode) {
     extern __shared__ __align__(128) unsigned char s_sa[];
     unsigned char *sQ = s_sa;                                                      // 128 x 128 fp32 = 64 KB
     unsigned char *sK = s_sa + 64 * 1024;                                          // 256 x 128 fp32 = 128 KB (later V^T)
@@ -255,6 +162,10 @@ k_self_attention_tc(const float *__restrict__ qkv, float *__restrict__ out, int 
                 tmem_st32(tmem_S + lane_addr + c, v);
             }
             s_inv[row] = 1.0f / sum;
+            if (stats) {   // what the backward needs to rebuild exactly these probabilities: (max * scale * log2 e, 1 / sum)
+                float2 *st = reinterpret_cast<float2 *>(stats) + ((size_t)img * n_heads + head) * kSaL + half * 128 + row;
+                *st = make_float2(mb, 1.0f / sum);
+            }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -293,9 +204,9 @@ k_self_attention_tc(const float *__restrict__ qkv, float *__restrict__ out, int 
 
 }  // namespace ps
 
-extern "C" PS_API int ps_self_attention_forward(int32_t n_images, int32_t tokens, int32_t heads, int32_t dim_head,
-                                                const float *qkv, float scale, float *out, int32_t debug_mode,
-                                                void *stream) {
+static int self_attention_forward_impl(int32_t n_images, int32_t tokens, int32_t heads, int32_t dim_head,
+                                       const float *qkv, float scale, float *out, float *stats, int32_t debug_mode,
+                                       void *stream) {
     using namespace ps;
     if (n_images < 1 || heads < 1 || heads > 16 || !qkv || !out) {
         set_error("ps_self_attention_forward: bad argument");
@@ -313,7 +224,20 @@ extern "C" PS_API int ps_self_attention_forward(int32_t n_images, int32_t tokens
     }
     dim3 grid(2, heads, n_images);
     k_self_attention_tc<<<grid, kSaThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-        qkv, out, heads, scale * 1.4426950408889634f, debug_mode);
+        qkv, out, stats, heads, scale * 1.4426950408889634f, debug_mode);
     PS_LAUNCH_CHECK("k_self_attention_tc");
     return PS_OK;
+}
+
+extern "C" PS_API int ps_self_attention_forward(int32_t n_images, int32_t tokens, int32_t heads, int32_t dim_head,
+                                                const float *qkv, float scale, float *out, int32_t debug_mode,
+                                                void *stream) {
+    return self_attention_forward_impl(n_images, tokens, heads, dim_head, qkv, scale, out, nullptr, debug_mode, stream);
+}
+
+extern "C" PS_API int ps_self_attention_forward_stats(int32_t n_images, int32_t tokens, int32_t heads, int32_t dim_head,
+                                                      const float *qkv, float scale, float *out, float *stats,
+                                                      void *stream) {
+    if (!stats) { ps::set_error("ps_self_attention_forward_stats: stats is NULL"); return PS_ERR_INVALID_ARGUMENT; }
+    return self_attention_forward_impl(n_images, tokens, heads, dim_head, qkv, scale, out, stats, 0, stream);
 }

@@ -47,6 +47,13 @@ class EncoderTailCfg:
             self.opacity_mapping = OpacityMappingCfg(0.0, 0.0, 1)          # epipolar.yaml:6-9
 
 
+def _wh(w: int, h: int, device) -> Tensor:
+    """float32 [w, h] on `device`, built by fill kernels (torch.tensor(...) from a Python tuple is a pageable
+    host-to-device copy, which a CUDA-graph capture rejects)."""
+    return torch.cat([torch.full((1,), float(w), dtype=torch.float32, device=device),
+                      torch.full((1,), float(h), dtype=torch.float32, device=device)])
+
+
 class EncoderEpipolarTail(nn.Module):
     def __init__(self, cfg: EncoderTailCfg) -> None:
         super().__init__()
@@ -83,7 +90,7 @@ class EncoderEpipolarTail(nn.Module):
         gaussians = self.to_gaussians(features)
         gaussians = gaussians.reshape(*gaussians.shape[:-1], self.cfg.num_surfaces, -1)   # "... (srf c) -> ... srf c"
         offset_xy = gaussians[..., :2].sigmoid()
-        pixel_size = 1 / torch.tensor((w, h), dtype=torch.float32, device=device)
+        pixel_size = 1 / _wh(w, h, device)            # (no host->device copy: the step must be graph-capturable)
         xy_ray = xy_ray + (offset_xy - 0.5) * pixel_size
         g = self.gaussian_adapter(
             context["extrinsics"][:, :, None, None, None], context["intrinsics"][:, :, None, None, None],

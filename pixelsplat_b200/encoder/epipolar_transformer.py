@@ -12,6 +12,7 @@ self-attention stay library code (cuDNN / cuBLAS through torch).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from functools import partial
 from typing import Optional
@@ -67,6 +68,7 @@ class EpipolarTransformer(nn.Module):
             num_context_views = _num_context_views_from_reference_cfg()
         self.cfg = cfg
         self.num_context_views = num_context_views
+        self.conv_channels_last = os.environ.get("PIXELSPLAT_B200_CONV_NHWC", "0") == "1"
         self.epipolar_sampler = EpipolarSampler(num_context_views, cfg.num_samples)
         if cfg.num_octaves > 0:
             pe = PositionalEncoding(cfg.num_octaves)
@@ -106,7 +108,13 @@ class EpipolarTransformer(nn.Module):
         features = x.reshape(b, v, h, w, c).permute(0, 1, 4, 2, 3)
 
         if self.upscaler is not None:
-            f = self.upscaler(features.flatten(0, 1))
+            x = features.flatten(0, 1)
+            if self.conv_channels_last:
+                # cuDNN's tensor-core kernels for the 7x7 refinement convolutions (the largest item of the step,
+                # SURVEY.md 8 row f-2) are NHWC kernels; handing them NHWC activations removes the layout
+                # transposes cuDNN otherwise wraps around every call.  Values are unchanged.
+                x = x.contiguous(memory_format=torch.channels_last)
+            f = self.upscaler(x)
             f = self.upscale_refinement(f) + f
             features = f.unflatten(0, (b, v))
         return features, sampling

@@ -179,7 +179,9 @@ class GaussianAdapter(nn.Module):
         scale_min, scale_max = self.cfg.gaussian_scale_min, self.cfg.gaussian_scale_max
         scales = scale_min + (scale_max - scale_min) * scales.sigmoid()
         h, w = image_shape
-        pixel_size = (1 / torch.tensor((w, h), dtype=torch.float32, device=device)).to(intrinsics.dtype)
+        wh = torch.cat([torch.full((1,), float(w), dtype=torch.float32, device=device),
+                        torch.full((1,), float(h), dtype=torch.float32, device=device)])   # no H2D copy
+        pixel_size = (1 / wh).to(intrinsics.dtype)
         multiplier = self.get_scale_multiplier(intrinsics, pixel_size)
         scales = scales * depths[..., None] * multiplier[..., None]
         rotations = rotations / (rotations.norm(dim=-1, keepdim=True) + eps)

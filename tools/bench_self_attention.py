@@ -55,13 +55,28 @@ def main():
         t_tf32 = timed(explicit)
         torch.backends.cuda.matmul.allow_tf32 = False
         t_sdpa = timed(sdpa)
+        # forward + backward: the tcgen05 pair vs the round-1 backward (fp32 torch GEMMs) behind the same forward
+        import os
+        qg = qkv.clone().requires_grad_(True)
+        wgt = torch.randn(n, L, heads * d, device=dev)
+
+        def fb():
+            qg.grad = None
+            (sa.self_attention_tc(qg, heads, scale) * wgt).sum().backward()
+
+        os.environ["PIXELSPLAT_B200_SELF_ATTENTION_BWD"] = "tc"
+        t_fb_tc = timed(fb, iters=30, warmup=5)
+        os.environ["PIXELSPLAT_B200_SELF_ATTENTION_BWD"] = "torch"
+        t_fb_torch = timed(fb, iters=30, warmup=5)
+        os.environ["PIXELSPLAT_B200_SELF_ATTENTION_BWD"] = "tc"
         ref = explicit().double()
         err = float((sa.self_attention_tc(qkv, heads, scale).double() - ref).abs().max() / ref.abs().max())
         flops = n * heads * 2 * (2.0 * L * L * d)
         rows.append({"images": n, "ctas": 2 * heads * n, "tcgen05_us": t_tc, "torch_fp32_us": t_fp32,
-                     "torch_tf32_us": t_tf32, "torch_sdpa_us": t_sdpa, "tcgen05_tflops": flops / t_tc * 1e-6,
+                     "torch_tf32_us": t_tf32, "torch_sdpa_us": t_sdpa,
+                     "fwd_bwd_tcgen05_us": t_fb_tc, "fwd_bwd_torch_backward_us": t_fb_torch, "tcgen05_tflops": flops / t_tc * 1e-6,
                      "rel_err_vs_torch_fp32": err})
-    print(json.dumps({"what": "self-attention 256 tokens x 4 heads x 128, forward", "rows": rows}))
+    print(json.dumps({"what": "self-attention 256 tokens x 4 heads x 128; forward, and forward + backward (incl. the loss ops)", "rows": rows}))
 
 
 if __name__ == "__main__":

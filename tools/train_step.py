@@ -138,6 +138,8 @@ def main():
                 run()
             torch.cuda.synchronize()
         except Exception as exc:                   # report and keep measuring eagerly
+            import traceback
+            traceback.print_exc()
             launch = f"eager python (graph capture failed: {type(exc).__name__}: {str(exc)[:200]})"
             torch.cuda.synchronize()
     if world > 1:
@@ -167,6 +169,15 @@ def main():
             "peak_gib": torch.cuda.max_memory_allocated() / 2 ** 30, "loss": float(loss),
             "n_gpus": world, "data": "synthetic", "dtype": "f32"}))
     if world > 1:
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+        if args.graph:
+            # a captured graph holds NCCL work of this communicator; tearing the process group down underneath it
+            # blocks (observed: destroy_process_group never returned).  The measurement is done: leave directly.
+            sys.stdout.flush()
+            sys.stderr.flush()
+            import os
+            os._exit(0)
         torch.distributed.destroy_process_group()
 
 
