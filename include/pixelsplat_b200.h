@@ -134,6 +134,9 @@ typedef struct ps_raster_layout {
                              alpha >= 1/255 box -- the compositor's cull record                */
     size_t color;         /* image: f32 [S*V*3*H*W] copy of the rendered colour (the backward's
                              forward-order prefix form needs C . dL/dC per pixel)              */
+    size_t block_hits;    /* binning: u32x2 [8 * capacity] per-(tile, 8x4 block, run) hit lists (position, Gaussian)
+                             the composite forward leaves for its backward; 0 when not kept (large capacity)   */
+    size_t run_hits;      /* binning: u32 [S*V*tiles*8*4] their lengths                                        */
     size_t run_state;     /* image: f32x4 [S*V*3*H*W] (T, Cr, Cg, Cb) in front of list runs 1..3 when the
                              compositor cuts a tile's list into runs (small batches)            */
 } ps_raster_layout;

@@ -47,8 +47,16 @@ struct LossEpilogue {
 
 constexpr int kMaxSegments = 4;   // list runs per warp task (raster_composite2.cu)
 
+// The composite forward's per-(tile, block, run) hit lists, kept for the backward (binning state).  Run k of block
+// `sub` of tile segment `seg` owns hits[(tile_start[seg] * 8 + sub * tile_count[seg]) + run_begin ...] (a run cannot
+// have more hits than entries), its length is run_hits[(seg * 8 + sub) * kMaxSegments + k].
+struct HitLists {
+    uint2 *hits;              // (list position, Gaussian id)
+    uint32_t *run_hits;
+};
+
 struct Dims {
-    int S, V, P, M, deg, sh_layout, cov_layout, H, W, gx, gy, tiles, sh_basis, segK;
+    int S, V, P, M, deg, sh_layout, cov_layout, H, W, gx, gy, tiles, sh_basis, segK, hit_lists;
     long long capacity;
 };
 
@@ -117,10 +125,11 @@ int launch_binning(const Dims &d, const Geom &g, unsigned long long *keys,
                    unsigned long long *keys_alt, int sort_impl, int segment_hint, cudaStream_t st);
 int launch_composite_forward(const Dims &d, const Inputs &in, const Geom &g,
                              const unsigned long long *keys, const ImageState &img,
-                             float *out_color, const LossEpilogue &loss, cudaStream_t st);
+                             float *out_color, const LossEpilogue &loss, const HitLists &hl, cudaStream_t st);
 int launch_composite_backward(const Dims &d, const Inputs &in, const Geom &g,
                               const unsigned long long *keys, const ImageState &img,
-                              const float *d_color, const ViewGrads &vg, const LossEpilogue &loss, cudaStream_t st);
+                              const float *d_color, const ViewGrads &vg, const LossEpilogue &loss, const HitLists &hl,
+                              cudaStream_t st);
 // legacy CTA-per-tile compositor (round 1), kept selectable for A/B measurements
 int launch_composite_forward_v1(const Dims &d, const Inputs &in, const Geom &g,
                                 const unsigned long long *keys, const ImageState &img,
@@ -130,7 +139,8 @@ int launch_composite_backward_v1(const Dims &d, const Inputs &in, const Geom &g,
                                  const float *d_color, const ViewGrads &vg, cudaStream_t st);
 int composite_impl();   // 1 = legacy, 2 = warp-task compositor (env PIXELSPLAT_B200_COMPOSITE, default 2)
 int set_composite_option(int which, int value);   // 0: impl (1 | 2), 1: segments (0 = auto | 1 | 2 | 4)
-int composite_segments(long long tasks);   // list runs per task (1, 2, 4) for a batch of `tasks` warp tasks
+int composite_segments(long long tasks);
+bool composite_hit_lists(long long capacity);      // keep the forward's hit lists for the backward?   // list runs per task (1, 2, 4) for a batch of `tasks` warp tasks
 int launch_preprocess_backward(const Dims &d, const Inputs &in, const Geom &g, const ViewGrads &vg,
                                const ps_raster_grads &out, cudaStream_t st);
 int launch_gradient_fill(const Dims &d, const ps_raster_grads &out, cudaStream_t st);

@@ -127,6 +127,7 @@ static Dims make_dims(const ps_raster_desc *d) {
     r.capacity = d->instance_capacity;
     r.sh_basis = d->sh_basis;
     r.segK = composite_segments((long long)r.S * r.V * r.tiles * 8);
+    r.hit_lists = composite_hit_lists(r.capacity) ? 1 : 0;
     return r;
 }
 
@@ -156,6 +157,13 @@ static Layout make_layout(const ps_raster_desc *d) {
     o = 0;
     L.off.keys = take((size_t)m.capacity * 8);
     L.off.keys_alt = take((size_t)m.capacity * 8);
+    // per-(tile, block, run) hit lists written by the composite forward for its backward (8 x the instances in the
+    // worst case: only kept when that stays small; the backward culls for itself otherwise)
+    L.off.block_hits = L.off.run_hits = 0;
+    if (m.hit_lists) {
+        L.off.block_hits = take((size_t)m.capacity * 8 * 8);
+        L.off.run_hits = take((size_t)m.S * m.V * m.tiles * 8 * kMaxSegments * 4);
+    }
     L.sizes.binning_bytes = o;
     o = 0;
     L.off.final_T = take(px * 4);
@@ -327,7 +335,12 @@ static int raster_forward_impl(const ps_raster_desc *desc, const ps_raster_input
         PS_CUDA_CHECK(cudaMemcpyAsync(n_instances_host, g.n_instances, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     if (le.sums)
         PS_CUDA_CHECK(cudaMemsetAsync(le.sums, 0, sizeof(float) * 2 * kLossSlots * (size_t)d.S * d.V, st));
-    if ((rc = launch_composite_forward(d, I, g, keys, img, out_color, le, st))) return rc;
+    HitLists hl{nullptr, nullptr};
+    if (d.hit_lists) {
+        hl.hits = reinterpret_cast<uint2 *>(static_cast<char *>(state->binning) + L.off.block_hits);
+        hl.run_hits = reinterpret_cast<uint32_t *>(static_cast<char *>(state->binning) + L.off.run_hits);
+    }
+    if ((rc = launch_composite_forward(d, I, g, keys, img, out_color, le, hl, st))) return rc;
     mark(kMarkCompositeFwd, st);
     if (out_radii)
         PS_CUDA_CHECK(cudaMemcpyAsync(out_radii, g.radii, sizeof(int32_t) * (size_t)d.S * d.V * d.P,
@@ -395,7 +408,12 @@ static int raster_backward_impl(const ps_raster_desc *desc, const ps_raster_inpu
     PS_CUDA_CHECK(cudaEventRecord(sc->join, sc->side));
     PS_CUDA_CHECK(cudaMemsetAsync(scratch, 0, L.sizes.backward_bytes, st));
     mark(kMarkBwdZero, st);
-    if ((rc = launch_composite_backward(d, I, g, keys, img, d_color, vg, le, st))) return rc;
+    HitLists hl{nullptr, nullptr};
+    if (d.hit_lists) {
+        hl.hits = reinterpret_cast<uint2 *>(static_cast<char *>(state->binning) + L.off.block_hits);
+        hl.run_hits = reinterpret_cast<uint32_t *>(static_cast<char *>(state->binning) + L.off.run_hits);
+    }
+    if ((rc = launch_composite_backward(d, I, g, keys, img, d_color, vg, le, hl, st))) return rc;
     mark(kMarkCompositeBwd, st);
     PS_CUDA_CHECK(cudaStreamWaitEvent(st, sc->join, 0));   // join
     if ((rc = launch_preprocess_backward(d, I, g, vg, *grads, st))) return rc;

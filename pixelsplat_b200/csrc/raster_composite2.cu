@@ -203,7 +203,7 @@ __device__ __forceinline__ uint32_t queue_pad(HitQueue &q, uint32_t tail, int la
 // Returns the number of hits; they become readable in the queue after the NEXT cull_park.
 __device__ __forceinline__ int cull_step(CullPipe &p, const Geom &geo, const TaskGeom &t,
                                          const unsigned long long *__restrict__ keys, uint32_t n, uint32_t c,
-                                         uint32_t tail, int lane) {
+                                         uint32_t tail, int lane, uint2 *__restrict__ hit_out = nullptr) {
     const uint32_t pos = c * 32u + (uint32_t)lane;
     const float4 cr = p.cr;
     const bool hit = pos < n && (cr.x + cr.z >= t.rx0) && (cr.x - cr.z <= t.rx1) && (cr.y + cr.w >= t.ry0) &&
@@ -211,9 +211,11 @@ __device__ __forceinline__ int cull_step(CullPipe &p, const Geom &geo, const Tas
     const uint32_t mask = __ballot_sync(0xffffffffu, hit);
     if (hit) {
         p.h_pending = true;
-        p.h_slot = (tail + (uint32_t)__popc(mask & ((1u << lane) - 1u))) & (kQ - 1);
+        const uint32_t idx = tail + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+        p.h_slot = idx & (kQ - 1);
         p.h_g = p.g;
         p.h_pos = t.run_begin + pos;          // position in the TILE's list (n_contrib semantics)
+        if (hit_out) hit_out[idx] = make_uint2(p.h_pos, p.g);     // the backward walks this list instead of culling
         p.h_xy = make_float2(cr.x, cr.y);
         p.h_co = geo.conic_opacity[t.gbase + p.g];
         p.h_rgb = geo.rgb[t.gbase + p.g];
@@ -276,8 +278,8 @@ __device__ __forceinline__ void fwd_blend4(const HitQueue &q, uint32_t base, con
 }
 
 // Front-to-back blend of the warp's run [t.run_begin, t.run_begin + t.run_len) onto the per-lane state px.
-__device__ __forceinline__ void fwd_run(const Geom &geo, const TaskGeom &t, const unsigned long long *__restrict__ keys,
-                                        HitQueue &q, FwdPixel &px, int lane) {
+__device__ __forceinline__ uint32_t fwd_run(const Geom &geo, const TaskGeom &t, const unsigned long long *__restrict__ keys,
+                                            HitQueue &q, FwdPixel &px, int lane, uint2 *__restrict__ hit_out = nullptr) {
     const uint32_t n = t.run_len;
     float T = px.T, Cr = px.Cr, Cg = px.Cg, Cb = px.Cb;
     uint32_t last = px.last;
@@ -289,24 +291,25 @@ __device__ __forceinline__ void fwd_run(const Geom &geo, const TaskGeom &t, cons
     for (uint32_t c = 0; c <= nchunks; ++c) {          // one extra iteration drains the last parked hits
         cull_park<false>(p, q, nullptr, t);
         uint32_t avail = tail;                         // parked so far
-        if (c < nchunks) tail += (uint32_t)cull_step(p, geo, t, keys, n, c, tail, lane);
+        if (c < nchunks) tail += (uint32_t)cull_step(p, geo, t, keys, n, c, tail, lane, hit_out);
         else avail = queue_pad(q, tail, lane);
         // whole groups of four (their power / exp evaluations are independent, only the transmittance chains)
         while (avail - head >= 4u) {
             fwd_blend4(q, head & (kQ - 1), t, T, Cr, Cg, Cb, last, done, stopped);
             head += 4u;
         }
-        if (__all_sync(0xffffffffu, done)) break;
+        if (__all_sync(0xffffffffu, done)) break;     // (hits beyond this point are behind every pixel's last contributor)
         __syncwarp();
     }
     __syncwarp();
     px.T = T; px.Cr = Cr; px.Cg = Cg; px.Cb = Cb; px.last = last; px.done = done; px.stopped = stopped;
+    return tail;
 }
 
 template <int K>
 __global__ void __launch_bounds__(kFwdWarps * 32, PS_FWD_MIN_CTAS)
 k_composite_fwd2(Dims d, Geom geo, const float *__restrict__ bg_all, const unsigned long long *__restrict__ keys,
-                 ImageState img, float *__restrict__ out_color, LossEpilogue loss) {
+                 ImageState img, float *__restrict__ out_color, LossEpilogue loss, HitLists hl) {
     __shared__ HitQueue s_q[kFwdWarps];
     __shared__ float4 s_ct[K > 1 ? kFwdWarps : 1][32];      // a run's (Cr, Cg, Cb, T)
     __shared__ uint32_t s_last[K > 1 ? kFwdWarps : 1][32];   // its last contributor | stopped << 31
@@ -326,7 +329,14 @@ k_composite_fwd2(Dims d, Geom geo, const float *__restrict__ bg_all, const unsig
     px.T = 1.0f; px.Cr = px.Cg = px.Cb = 0.0f;
     px.last = 0; px.stopped = false;
     px.done = !valid || !t.inside;
-    if (valid) fwd_run(geo, t, keys, q, px, lane);
+    if (valid) {
+        const long long task = (long long)blockIdx.x * kTasksPerCta + warp / K;
+        uint2 *hit_out = nullptr;
+        if (hl.hits)   // this run's slice of the block's region (a run has at most run_len hits)
+            hit_out = hl.hits + ((size_t)t.start * 8 + (size_t)(task & 7) * t.count + t.run_begin);
+        const uint32_t nh = fwd_run(geo, t, keys, q, px, lane, hit_out);
+        if (hl.run_hits && lane == 0) hl.run_hits[task * kMaxSegments + run] = nh;
+    }
 
     if (K > 1) {
         s_ct[warp][lane] = make_float4(px.Cr, px.Cg, px.Cb, px.T);
@@ -495,7 +505,7 @@ __device__ __forceinline__ void bwd_batch(BwdSmem &sm, BwdPixel &px, const TaskG
 template <int K>
 __global__ void __launch_bounds__(kBwdWarps * 32, 6)
 k_composite_bwd2(Dims d, Geom geo, const float *__restrict__ bg_all, const unsigned long long *__restrict__ keys,
-                 ImageState img, const float *__restrict__ d_color, ViewGrads vg, LossEpilogue loss) {
+                 ImageState img, const float *__restrict__ d_color, ViewGrads vg, LossEpilogue loss, HitLists hl) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     constexpr int kTasksPerCta = kBwdWarps / K;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -540,17 +550,56 @@ k_composite_bwd2(Dims d, Geom geo, const float *__restrict__ bg_all, const unsig
     const float kx = kLn2 * 0.5f * (float)d.W, ky = kLn2 * 0.5f * (float)d.H;
     (void)bg_all;
 
-    CullPipe p;
-    cull_prologue(p, geo, t, keys, n, lane);
     uint32_t head = 0, tail = 0;
-    const uint32_t nchunks = (n + 31u) >> 5;
-    for (uint32_t c = 0; c <= nchunks; ++c) {
-        cull_park<true>(p, sm.q, sm.d0, t);
-        const uint32_t avail = tail;
-        if (c < nchunks) tail += (uint32_t)cull_step(p, geo, t, keys, n, c, tail, lane);
-        while (avail - head >= (uint32_t)kBatch) {
-            bwd_batch<true>(sm, px, t, vg, head, kBatch, kx, ky, lane);
-            head += kBatch;
+    if (hl.hits) {
+        // ---- the forward left this run's hit list: no cull, every lane parks a hit
+        const long long task = (long long)blockIdx.x * kTasksPerCta + warp / K;
+        const uint2 *__restrict__ hits = hl.hits + ((size_t)t.start * 8 + (size_t)(task & 7) * t.count + t.run_begin);
+        const uint32_t nh = n ? hl.run_hits[task * kMaxSegments + run] : 0u;
+        uint2 hnext = make_uint2(0u, 0u);
+        if ((uint32_t)lane < nh) hnext = hits[lane];
+        for (uint32_t h0 = 0; h0 < nh; h0 += 32u) {
+            const uint2 hcur = hnext;
+            const bool live = h0 + (uint32_t)lane < nh && hcur.x < nmax;     // nothing behind the last contributor
+            if (h0 + 32u + (uint32_t)lane < nh) hnext = hits[h0 + 32u + lane];
+            float4 cr = make_float4(0.0f, 0.0f, 0.0f, 0.0f), co = cr, rgb = cr;
+            if (live) {
+                cr = geo.cull[t.gbase + hcur.y];
+                co = geo.conic_opacity[t.gbase + hcur.y];
+                rgb = geo.rgb[t.gbase + hcur.y];
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, live);
+            if (live) {
+                const uint32_t slot = (tail + (uint32_t)__popc(m & ((1u << lane) - 1u))) & (kQ - 1);
+                const float qa = -0.5f * kLog2e * co.x, qb = -kLog2e * co.y, qc = -0.5f * kLog2e * co.z;
+                const float dx0 = cr.x - t.rx0, dy0 = cr.y - t.ry0;
+                const float ax = qa * dx0, cy = qc * dy0;
+                sm.q.r0[slot] = make_float4(fmaf(ax, dx0, fmaf(cy, dy0, qb * dx0 * dy0)), -(2.0f * ax + qb * dy0),
+                                            -(2.0f * cy + qb * dx0), co.w);
+                sm.q.r1[slot] = make_float4(qa, qb, qc, __uint_as_float(hcur.x));
+                sm.q.r2[slot] = make_float4(rgb.x, rgb.y, rgb.z, __uint_as_float(hcur.y));
+                sm.d0[slot] = make_float2(dx0, dy0);
+            }
+            tail += (uint32_t)__popc(m);
+            __syncwarp();
+            while (tail - head >= (uint32_t)kBatch) {
+                bwd_batch<true>(sm, px, t, vg, head, kBatch, kx, ky, lane);
+                head += kBatch;
+            }
+            if (m != 0xffffffffu) break;                                      // the list is ordered by position
+        }
+    } else {
+        CullPipe p;
+        cull_prologue(p, geo, t, keys, n, lane);
+        const uint32_t nchunks = (n + 31u) >> 5;
+        for (uint32_t c = 0; c <= nchunks; ++c) {
+            cull_park<true>(p, sm.q, sm.d0, t);
+            const uint32_t avail = tail;
+            if (c < nchunks) tail += (uint32_t)cull_step(p, geo, t, keys, n, c, tail, lane);
+            while (avail - head >= (uint32_t)kBatch) {
+                bwd_batch<true>(sm, px, t, vg, head, kBatch, kx, ky, lane);
+                head += kBatch;
+            }
         }
     }
     if (tail != head) {
@@ -580,31 +629,33 @@ int set_composite_option(int which, int value) {
 
 template <int K>
 static int launch_fwd(const Dims &d, const Inputs &in, const Geom &g, const unsigned long long *keys,
-                      const ImageState &img, float *out_color, const LossEpilogue &loss, cudaStream_t st) {
+                      const ImageState &img, float *out_color, const LossEpilogue &loss, const HitLists &hl,
+                      cudaStream_t st) {
     const long long tasks = (long long)d.S * d.V * d.tiles * 8;
     constexpr int per_cta = kFwdWarps / K;
-    k_composite_fwd2<K><<<(unsigned)((tasks + per_cta - 1) / per_cta), kFwdWarps * 32, 0, st>>>(d, g, in.bg, keys, img, out_color, loss);
+    k_composite_fwd2<K><<<(unsigned)((tasks + per_cta - 1) / per_cta), kFwdWarps * 32, 0, st>>>(d, g, in.bg, keys, img, out_color, loss, hl);
     PS_LAUNCH_CHECK("k_composite_fwd2");
     return PS_OK;
 }
 
 int launch_composite_forward(const Dims &d, const Inputs &in, const Geom &g, const unsigned long long *keys,
-                             const ImageState &img, float *out_color, const LossEpilogue &loss, cudaStream_t st) {
+                             const ImageState &img, float *out_color, const LossEpilogue &loss, const HitLists &hl,
+                             cudaStream_t st) {
     if (composite_impl() == 1) {
         if (loss.target || !out_color) { set_error("the legacy compositor has no loss epilogue"); return PS_ERR_UNSUPPORTED; }
         return launch_composite_forward_v1(d, in, g, keys, img, out_color, st);
     }
     switch (d.segK) {
-        case 4: return launch_fwd<4>(d, in, g, keys, img, out_color, loss, st);
-        case 2: return launch_fwd<2>(d, in, g, keys, img, out_color, loss, st);
-        default: return launch_fwd<1>(d, in, g, keys, img, out_color, loss, st);
+        case 4: return launch_fwd<4>(d, in, g, keys, img, out_color, loss, hl, st);
+        case 2: return launch_fwd<2>(d, in, g, keys, img, out_color, loss, hl, st);
+        default: return launch_fwd<1>(d, in, g, keys, img, out_color, loss, hl, st);
     }
 }
 
 template <int K>
 static int launch_bwd(const Dims &d, const Inputs &in, const Geom &g, const unsigned long long *keys,
                       const ImageState &img, const float *d_color, const ViewGrads &vg, const LossEpilogue &loss,
-                      cudaStream_t st) {
+                      const HitLists &hl, cudaStream_t st) {
     const long long tasks = (long long)d.S * d.V * d.tiles * 8;
     constexpr int per_cta = kBwdWarps / K;
     const size_t smem = sizeof(BwdSmem) * kBwdWarps;
@@ -612,22 +663,22 @@ static int launch_bwd(const Dims &d, const Inputs &in, const Geom &g, const unsi
     if (first_use_on_device(attr_devices)) {
         PS_CUDA_CHECK(cudaFuncSetAttribute(k_composite_bwd2<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    k_composite_bwd2<K><<<(unsigned)((tasks + per_cta - 1) / per_cta), kBwdWarps * 32, smem, st>>>(d, g, in.bg, keys, img, d_color, vg, loss);
+    k_composite_bwd2<K><<<(unsigned)((tasks + per_cta - 1) / per_cta), kBwdWarps * 32, smem, st>>>(d, g, in.bg, keys, img, d_color, vg, loss, hl);
     PS_LAUNCH_CHECK("k_composite_bwd2");
     return PS_OK;
 }
 
 int launch_composite_backward(const Dims &d, const Inputs &in, const Geom &g, const unsigned long long *keys,
                               const ImageState &img, const float *d_color, const ViewGrads &vg,
-                              const LossEpilogue &loss, cudaStream_t st) {
+                              const LossEpilogue &loss, const HitLists &hl, cudaStream_t st) {
     if (composite_impl() == 1) {
         if (!d_color) { set_error("the legacy compositor has no loss epilogue"); return PS_ERR_UNSUPPORTED; }
         return launch_composite_backward_v1(d, in, g, keys, img, d_color, vg, st);
     }
     switch (d.segK) {
-        case 4: return launch_bwd<4>(d, in, g, keys, img, d_color, vg, loss, st);
-        case 2: return launch_bwd<2>(d, in, g, keys, img, d_color, vg, loss, st);
-        default: return launch_bwd<1>(d, in, g, keys, img, d_color, vg, loss, st);
+        case 4: return launch_bwd<4>(d, in, g, keys, img, d_color, vg, loss, hl, st);
+        case 2: return launch_bwd<2>(d, in, g, keys, img, d_color, vg, loss, hl, st);
+        default: return launch_bwd<1>(d, in, g, keys, img, d_color, vg, loss, hl, st);
     }
 }
 
@@ -641,6 +692,20 @@ int composite_segments(long long tasks) {
     if (composite_impl() == 1) return 1;
     if (g_segments) return g_segments;
     return tasks <= 2048 ? 4 : tasks <= 4096 ? 2 : 1;
+}
+
+// The forward's hit lists cost 64 bytes of binning state per unit of instance capacity: kept while that is at most
+// 512 MB (every configuration of BASELINE.json at batch 1-2), dropped beyond (the backward then culls for itself).
+// PIXELSPLAT_B200_HIT_LISTS = 0 | 1 forces it (A/B runs); the legacy compositor never uses them.
+bool composite_hit_lists(long long capacity) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char *e = getenv("PIXELSPLAT_B200_HIT_LISTS");
+        forced = (e && (e[0] == '0' || e[0] == '1') && e[1] == 0) ? (e[0] - '0') : 2;
+    }
+    if (composite_impl() == 1) return false;
+    if (forced != 2) return forced == 1;
+    return capacity * 64 <= (512ll << 20);
 }
 
 }  // namespace ps
