@@ -64,11 +64,13 @@ for n, a in sorted(agg.items(), key=lambda kv: -kv[1]["gpu__time_duration.sum"])
 
 if json_out:
     out = {"source": Path(path).name, "csrc_sha": csrc_sha(), "note": "per-launch means; ncu launch list (cold cache, serialised)"}
+    import re
     for n, a in agg.items():
         c = cnt[n]
-        if not n.startswith("ps::"):
+        if "ps::" not in n:
             continue
-        out[n.replace("ps::", "")] = {
+        key = re.sub(r"<.*>$", "", n.replace("void ", "").replace("ps::", "").strip())    # k_composite_bwd2<4> -> k_composite_bwd2
+        out[key] = {
             "launches": c, "us": a["gpu__time_duration.sum"] / c / 1e3, "warp_inst": a.get("smsp__inst_executed.sum", 0.0) / c,
             "dram_bytes": (a.get("dram__bytes_read.sum", 0.0) + a.get("dram__bytes_write.sum", 0.0)) / c,
             "warps_active_pct": a.get("sm__warps_active.avg.pct_of_peak_sustained_active", 0.0) / c,
