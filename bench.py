@@ -190,6 +190,48 @@ def algorithmic_bytes(P, M, N, vis, HW, cov_floats=9):
     }
 
 
+def build_roofline(stage_ms: dict, V: int, P: int, N: float, vis: float, HW: int, standard_workload: bool) -> dict:
+    """The `roofline` object of the bench line for the stage the live per-stage CUDA events found dominant.
+    Pure function of its arguments + profiles/kernel_metrics_V1.json + MEASURED_PEAKS.json (unit-tested on the CPU:
+    tests/test_abi_cpu.py)."""
+    ab = algorithmic_bytes(P, 25, N, vis, HW)
+    dom = max(stage_ms, key=stage_ms.get)
+    pk, pk_kind = peaks()
+    achieved = V * ab[dom] / (stage_ms[dom] * 1e-3) / 1e9
+    # Measured-by-ncu properties of the stage's kernel -- DRAM bytes and warp instructions per launch -- come
+    # from profiles/kernel_metrics_V1.json, written by tools/summarize_launches.py from an ncu launch list of
+    # THIS build (the file carries a hash of the CUDA sources; a stale file is ignored, never a literal here).
+    kern = {"composite_bwd": "k_composite_bwd2", "composite_fwd": "k_composite_fwd2",
+            "preprocess_bwd": "k_preprocess_bwd", "tile_sort": "k_tile_sort", "preprocess": "k_preprocess",
+            "count_scan_scatter": "k_scatter"}.get(dom)
+    if os.environ.get("PIXELSPLAT_B200_COMPOSITE", "") == "1" and kern:
+        kern = kern.replace("2", "")
+    prof, prof_note = kernel_profile()
+    kp = prof.get(kern) if (prof and standard_workload and kern) else None
+    if not (isinstance(kp, dict) and "warp_inst" in kp and "dram_bytes" in kp):
+        kp = None
+    traffic = kp["dram_bytes"] if kp else None
+    issue_frac = (kp["warp_inst"] / (stage_ms[dom] * 1e-3) / ISSUE_PEAK) if kp else None
+    hbm_frac = achieved / pk["hbm_gbs"]
+    bound = "issue" if (issue_frac is not None and issue_frac > hbm_frac) else "hbm"
+    return {"kernel": dom, "bound": bound, "achieved": achieved, "peak": pk["hbm_gbs"],
+            "unit": "GB/s", "frac": hbm_frac, "traffic": traffic,
+            "issue_frac": issue_frac,
+            "issue": None if kp is None else {
+                "warp_inst_per_launch": kp["warp_inst"], "peak_warp_inst_per_s": ISSUE_PEAK,
+                "achieved_warp_inst_per_s": kp["warp_inst"] / (stage_ms[dom] * 1e-3),
+                "warps_active_pct": kp.get("warps_active_pct")},
+            "profile": prof_note,
+            "note": "the composite is SIMT fp32 work on L2-resident gathers: its DRAM traffic is at or below the "
+                    "algorithmic bytes (no re-reads) and what bounds it is instruction issue, so `frac` (HBM) is "
+                    "small by construction and `issue_frac` (warp instructions / s over SMs x 4 x clock) is the "
+                    "roofline that moves; see profiles/README.md",
+            "peak_source": f"{pk_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+            "algorithmic_bytes_per_launch": V * ab[dom], "avg_launch_ms": stage_ms[dom],
+            "pair_evals_per_s": (V * N * 256 / (stage_ms[dom] * 1e-3) if dom.startswith("composite") else None),
+            "all_stages_gbs": {s: V * ab[s] / (stage_ms[s] * 1e-3) / 1e9 for s in STAGES if stage_ms[s] > 0}}
+
+
 def cpu_threads() -> int:
     """Threads used for the CPU arm: the oracle's per-tile tensors are small (256 x ~1.5k), and
     on a 128-core host torch's intra-op pool over-subscribes badly (measured: 325 s per view with
@@ -528,42 +570,8 @@ def main():
         N = im["num_instances"] / V
         vis = float((im["radii"] > 0).sum().item()) / V
         stats = {"instances_per_view": N, "visible_per_view": vis, "gaussians": P}
-        ab = algorithmic_bytes(P, 25, N, vis, IMAGE[0] * IMAGE[1])
-        dom = max(stage_ms, key=stage_ms.get)
-        pk, pk_kind = peaks()
-        achieved = V * ab[dom] / (stage_ms[dom] * 1e-3) / 1e9
-        # Measured-by-ncu properties of the stage's kernel -- DRAM bytes and warp instructions per launch -- come
-        # from profiles/kernel_metrics_V1.json, written by tools/summarize_launches.py from an ncu launch list of
-        # THIS build (the file carries a hash of the CUDA sources; a stale file is ignored, never a literal here).
-        kern = {"composite_bwd": "k_composite_bwd2", "composite_fwd": "k_composite_fwd2",
-                "preprocess_bwd": "k_preprocess_bwd", "tile_sort": "k_tile_sort", "preprocess": "k_preprocess",
-                "count_scan_scatter": "k_scatter"}.get(dom)
-        if os.environ.get("PIXELSPLAT_B200_COMPOSITE", "") == "1" and kern:
-            kern = kern.replace("2", "")
-        prof, prof_note = kernel_profile()
-        kp = prof.get(kern) if (prof and (args.image, args.context_views, V) == (256, 2, 1)) else None
-        traffic = kp["dram_bytes"] if kp else None
-        issue_frac = (kp["warp_inst"] / (stage_ms[dom] * 1e-3) / ISSUE_PEAK) if kp else None
-        hbm_frac = achieved / pk["hbm_gbs"]
-        bound = "issue" if (issue_frac is not None and issue_frac > hbm_frac) else "hbm"
-        roofline = {"kernel": dom, "bound": bound, "achieved": achieved, "peak": pk["hbm_gbs"],
-                    "unit": "GB/s", "frac": hbm_frac, "traffic": traffic,
-                    "issue_frac": issue_frac,
-                    "issue": None if kp is None else {
-                        "warp_inst_per_launch": kp["warp_inst"], "peak_warp_inst_per_s": ISSUE_PEAK,
-                        "achieved_warp_inst_per_s": kp["warp_inst"] / (stage_ms[dom] * 1e-3),
-                        "warps_active_pct": kp.get("warps_active_pct")},
-                    "profile": prof_note,
-                    "note": "the composite is SIMT fp32 work on L2-resident gathers: its DRAM traffic is at or below the "
-                            "algorithmic bytes (no re-reads) and what bounds it is instruction issue, so `frac` (HBM) is "
-                            "small by construction and `issue_frac` (warp instructions / s over SMs x 4 x clock) is the "
-                            "roofline that moves; see profiles/README.md",
-                    "peak_source": f"{pk_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
-                    "algorithmic_bytes_per_launch": V * ab[dom], "avg_launch_ms": stage_ms[dom],
-                    "pair_evals_per_s": (V * N * 256 / (stage_ms[dom] * 1e-3)
-                                         if dom.startswith("composite") else None),
-                    "all_stages_gbs": {s: V * ab[s] / (stage_ms[s] * 1e-3) / 1e9 for s in STAGES
-                                       if stage_ms[s] > 0}}
+        roofline = build_roofline(stage_ms, V, P, N, vis, IMAGE[0] * IMAGE[1],
+                                  standard_workload=(args.image, args.context_views, V) == (256, 2, 1))
     torch.cuda.synchronize()
 
     # ---------------- CPU baseline (rank 0, N=1 only)

@@ -132,3 +132,27 @@ def test_loss_module_matches_the_reference_formulas():
     psnr = L.compute_psnr(tgt.flatten(0, 1), pred.flatten(0, 1))
     sse_c = ((pred.clip(0, 1) - tgt.clip(0, 1)) ** 2).sum(dim=(2, 3, 4))
     assert torch.allclose(L.psnr_from_sse(sse_c, (8, 10)).flatten(), psnr, atol=1e-5)
+
+
+def test_bench_roofline_object_is_built_from_the_profile_file():
+    """bench.py's `roofline` (a pure function of the stage times and profiles/kernel_metrics_V1.json): traffic and
+    issue_frac come from the profile of the SAME CUDA sources, never from a literal; a stale or missing profile
+    yields nulls, not a crash."""
+    import json as _json
+    import bench
+    stage = {"preprocess": 0.032, "count_scan_scatter": 0.030, "tile_sort": 0.030, "composite_fwd": 0.069,
+             "grad_zero_fill": 0.019, "composite_bwd": 0.080, "preprocess_bwd": 0.049}
+    r = bench.build_roofline(stage, 1, 393216, 399057.0, 125628.0, 65536, standard_workload=True)
+    assert r["kernel"] == "composite_bwd" and r["unit"] == "GB/s" and 0 < r["frac"] < 1
+    assert r["algorithmic_bytes_per_launch"] == 399057 * (48 + 36) + 65536 * 20
+    prof_path = ROOT / "profiles" / "kernel_metrics_V1.json"
+    prof = _json.loads(prof_path.read_text())
+    if prof["csrc_sha"] == bench.csrc_sha():
+        kp = prof["k_composite_bwd2"]
+        assert r["traffic"] == kp["dram_bytes"] and r["bound"] == "issue"
+        assert abs(r["issue_frac"] - kp["warp_inst"] / 0.080e-3 / bench.ISSUE_PEAK) < 1e-12 and 0 < r["issue_frac"] < 1
+    else:   # sources changed after the capture: ignored, says so
+        assert r["traffic"] is None and r["issue_frac"] is None and "ignored" in r["profile"]
+    r2 = bench.build_roofline(stage, 4, 393216, 490518.0, 154705.0, 65536, standard_workload=False)
+    assert r2["traffic"] is None and r2["bound"] == "hbm"
+    _json.dumps(r), _json.dumps(r2)
