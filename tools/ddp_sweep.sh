@@ -1,7 +1,7 @@
 #!/bin/bash
 # configs[3]: the training step at N GPUs of this box, whole-step CUDA graph and eager.  usage: tools/ddp_sweep.sh N
-# (8 processes on a fresh box need ~2 minutes before the first step: torch import + NCCL init + cuDNN autotune; a
-#  150 s limit killed both 8-GPU runs of round 2 before they printed -- keep the limits generous)
+# (round 2: at 8 GPUs both runs printed NCCL's banner and then nothing until a 150 s limit -- 4 GPUs finish in ~20 s;
+#  cause not established, see DESIGN.md section 8 -- keep the limits generous when retrying)
 N=${1:-2}
 mkdir -p gpurun_out
 for mode in "--graph" ""; do
