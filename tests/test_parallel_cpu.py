@@ -79,18 +79,23 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.timeout(120)
-def test_gloo_world2_collectives():
-    world, port = 2, _free_port()
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 8])
+def test_gloo_collectives(world):
+    """world 2: the N > 1 path of every helper; world 8: the rank count of configs[3] -- the bucket-ordered
+    reducer must not depend on the number of ranks (round 2's 8-GPU runs went silent after NCCL initialisation;
+    this rules the host-side logic out)."""
+    port = _free_port()
     with mp.Manager() as mgr:
         out = mgr.dict()
         mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
         res = dict(out)
-    assert res[0][0] == res[1][0] == 2.0                 # max over ranks
-    assert res[0][1] == res[1][1] and res[0][1] >= 2     # several buckets
-    assert res[0][2] and res[1][2]
-    assert res[0][3] == pytest.approx(10.0)              # 2 ranks x 10 units / 2 s
-    assert res[0][4] and res[1][4]                       # GradientReducer (overlapped, bucket views)
+    assert len(res) == world
+    assert all(res[r][0] == float(world) for r in range(world))          # max over ranks of 1 + rank
+    assert len({res[r][1] for r in range(world)}) == 1 and res[0][1] >= 2   # several buckets, same count everywhere
+    assert all(res[r][2] for r in range(world))
+    assert res[0][3] == pytest.approx(10.0)                               # world ranks x 10 units / world s
+    assert all(res[r][4] for r in range(world))                           # GradientReducer (overlapped, bucket views)
 
 
 def test_bench_stdout_carries_only_the_result_line():
