@@ -156,3 +156,30 @@ def test_bench_roofline_object_is_built_from_the_profile_file():
     r2 = bench.build_roofline(stage, 4, 393216, 490518.0, 154705.0, 65536, standard_workload=False)
     assert r2["traffic"] is None and r2["bound"] == "hbm"
     _json.dumps(r), _json.dumps(r2)
+
+
+def test_launch_list_summary_writes_the_profile_bench_reads(tmp_path):
+    """tools/summarize_launches.py --json: kernel names are normalised (`void ps::k_composite_bwd2<4>(...)` ->
+    `k_composite_bwd2`), per-launch means are taken, and the CUDA-source hash is the one bench.py computes."""
+    import json as _json
+    import bench
+    rows = ['"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size",'
+            '"Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"']
+
+    def launch(i, name, ns, inst, rd, wr):
+        for m, u, v in (("gpu__time_duration.sum", "ns", ns), ("smsp__inst_executed.sum", "inst", inst),
+                        ("dram__bytes_read.sum", "byte", rd), ("dram__bytes_write.sum", "byte", wr)):
+            rows.append(f'"{i}","1","python","h","{name}","1","7","(128, 1, 1)","(10, 1, 1)","0","10.0","s","{m}","{u}","{v}"')
+
+    launch(0, "void ps::k_composite_bwd2<4>(ps::Dims, ps::Geom)", "70,000", "35,000,000", "36,000,000", "1,000")
+    launch(1, "void ps::k_composite_bwd2<4>(ps::Dims, ps::Geom)", "72,000", "35,000,000", "36,000,000", "3,000")
+    launch(2, "ps::k_preprocess(ps::Dims, ps::Inputs, ps::Geom, int)", "26,000", "9,000,000", "20,000,000", "4,000,000")
+    launch(3, "void at::native::vectorized_elementwise_kernel<4>(int)", "3,000", "100", "0", "0")
+    csv_path, out = tmp_path / "launches.csv", tmp_path / "metrics.json"
+    csv_path.write_text("==PROF== header line\n" + "\n".join(rows) + "\n")
+    subprocess.run([sys.executable, str(ROOT / "tools" / "summarize_launches.py"), str(csv_path), "0", "--json", str(out)],
+                   check=True, capture_output=True)
+    d = _json.loads(out.read_text())
+    assert d["csrc_sha"] == bench.csrc_sha() and set(k for k in d if k.startswith("k_")) == {"k_composite_bwd2", "k_preprocess"}
+    kb = d["k_composite_bwd2"]
+    assert kb["launches"] == 2 and abs(kb["us"] - 71.0) < 1e-9 and kb["warp_inst"] == 35e6 and kb["dram_bytes"] == 36002000.0
